@@ -1,0 +1,466 @@
+"""CPU oracle for the scan + top-k hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+(``vectordb_retrieval_b200``) never imports it and has no CPU fallback.
+
+Every function restates, in NumPy, the semantics of one piece of the reference
+(Human-Augment-Analytics/vectordb-retrieval); citations are ``path:line`` relative
+to the reference root.
+
+Pinning status
+--------------
+* NumPy paths (LinearSearcher, FaissSearcher LSH-rerank, Python LSH, recall_at_k):
+  PINNED - ``oracle/gen_golden.py`` imports the unmodified reference classes (behind
+  throw-away ``faiss`` / ``matplotlib`` import stubs) and writes their outputs to
+  ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this module against
+  those files, the reference's own KATs (tests/test_composite_algorithm.py:29-226)
+  and the published LSH recall 0.31914062499999996
+  (benchmark_results/benchmark_20260305_070532/random/lsh_results.json:46).
+* FAISS paths (ExactSearch/IndexFlat values, IVF k-means, IndexLSH codes):
+  PARITY UNPINNED - faiss-cpu (requirements.txt:9, ``>=1.7.4``, no lock) is not in the
+  reference tree and not installed.  ``faiss_flat_search`` / ``ivf_flat_search`` restate
+  FAISS's documented conventions (squared L2 ascending, raw inner product descending,
+  int64 labels, -1 padding) and are anchored on the reference's call sites
+  (src/algorithms/exact_search.py:23,38-39,78; src/algorithms/modular.py:277-286,536-548).
+"""
+from __future__ import annotations
+
+import math
+from collections import Counter, defaultdict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+# --------------------------------------------------------------------------- helpers
+def safe_normalize(matrix: np.ndarray) -> np.ndarray:
+    """Row L2-normalisation, zero rows stay zero (src/algorithms/modular.py:109-111,
+    src/algorithms/lsh.py:13-16)."""
+    norms = np.linalg.norm(matrix, axis=1, keepdims=True)
+    out = np.zeros_like(matrix)
+    np.divide(matrix, norms, out=out, where=norms > 0)
+    return out
+
+
+def _as_f32(x: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _sorted_topk(values: np.ndarray, limit: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Ascending top-``limit`` of each row with the deterministic (value, index) order.
+
+    The reference uses argpartition + argsort (modular.py:349-354), whose order among
+    exactly equal values is unspecified; (value, index) is one member of that class and
+    is what the CUDA path produces."""
+    n = values.shape[1]
+    if limit >= n:
+        part = np.broadcast_to(np.arange(n), values.shape).copy()
+    else:
+        part = np.argpartition(values, limit - 1, axis=1)[:, :limit]
+        # argpartition may cut a tie group at the boundary: pull in every index whose
+        # value equals the k-th value and keep the lowest indices.
+        kth = np.take_along_axis(values, part, axis=1).max(axis=1)
+        for r in np.nonzero((values <= kth[:, None]).sum(axis=1) > limit)[0]:
+            cand = np.nonzero(values[r] <= kth[r])[0]
+            order = np.lexsort((cand, values[r, cand]))[:limit]
+            part[r] = cand[order]
+    pv = np.take_along_axis(values, part, axis=1)
+    order = np.lexsort((part, pv), axis=1)
+    idx = np.take_along_axis(part, order, axis=1)
+    val = np.take_along_axis(pv, order, axis=1)
+    return val, idx
+
+
+def _pad(dist: np.ndarray, idx: np.ndarray, k: int, pad_value: float) -> Tuple[np.ndarray, np.ndarray]:
+    limit = dist.shape[1]
+    if limit < k:
+        dist = np.pad(dist, ((0, 0), (0, k - limit)), constant_values=pad_value)
+        idx = np.pad(idx, ((0, 0), (0, k - limit)), constant_values=-1)
+    return dist.astype(np.float32), idx.astype(np.int64)
+
+
+# --------------------------------------------------------------------------- exact: LinearSearcher
+def linear_search(base: np.ndarray, queries: np.ndarray, k: int, metric: str = "l2",
+                  query_block: int = 64) -> Tuple[np.ndarray, np.ndarray]:
+    """``LinearSearcher.batch_search`` (src/algorithms/modular.py:336-387).
+
+    l2     : difference-form squared distance in fp32, top-k, **sqrt** (modular.py:343-355)
+    ip     : ``Q @ V.T``, distance = -score (modular.py:368,381)
+    cosine : both sides ``safe_normalize``-d then as ip (modular.py:322-324,365-366)
+    k > N pads with (+inf, -1) (modular.py:357-359,382-384).
+    The reference materialises an nq x N x d temporary; this restatement blocks over
+    queries (same arithmetic per element, bounded memory)."""
+    base = _as_f32(base)
+    q = _as_f32(np.atleast_2d(queries))
+    n = base.shape[0]
+    if n == 0:
+        raise RuntimeError("LinearSearcher cannot operate on empty index")
+    limit = min(k, n)
+    out_d = np.empty((q.shape[0], limit), dtype=np.float32)
+    out_i = np.empty((q.shape[0], limit), dtype=np.int64)
+    if metric == "l2":
+        for s in range(0, q.shape[0], query_block):
+            blk = q[s:s + query_block]
+            diffs = base[None, :, :] - blk[:, None, :]
+            sq = np.sum(diffs ** 2, axis=2)
+            val, idx = _sorted_topk(sq, limit)
+            out_d[s:s + query_block] = np.sqrt(val)
+            out_i[s:s + query_block] = idx
+    elif metric in ("cosine", "ip"):
+        if metric == "cosine":
+            vb, vq = safe_normalize(base), safe_normalize(q)
+        else:
+            vb, vq = base, q
+        for s in range(0, q.shape[0], max(query_block, 256)):
+            scores = vq[s:s + max(query_block, 256)] @ vb.T
+            val, idx = _sorted_topk(-scores, limit)
+            out_d[s:s + max(query_block, 256)] = val
+            out_i[s:s + max(query_block, 256)] = idx
+    else:
+        raise ValueError(f"Unsupported metric '{metric}' for LinearSearcher")
+    return _pad(out_d, out_i, k, np.inf)
+
+
+# --------------------------------------------------------------------------- exact: faiss.IndexFlat
+def faiss_flat_search(base: np.ndarray, queries: np.ndarray, k: int, metric: str = "l2",
+                      base_block: int = 65536, query_block: int = 1024) -> Tuple[np.ndarray, np.ndarray]:
+    """``ExactSearch.batch_search`` -> ``faiss.IndexFlat.search``
+    (src/algorithms/exact_search.py:23,38-39,76-78).  [FAISS-upstream, parity unpinned]
+
+    metric == 'l2'  : squared L2, ascending.
+    anything else   : raw inner product on un-normalised vectors, descending (not negated)
+                      - this is the quirk at exact_search.py:23.
+    Missing results: label -1, distance +FLT_MAX (l2) / -FLT_MAX (ip).
+    Scores are formed FAISS-style, ``|x|^2 + |q|^2 - 2 q.x`` with one sgemm per block and
+    negatives clamped to 0, but accumulated in fp64 so this is the *exact* value the fp32
+    implementations approximate."""
+    base = _as_f32(base)
+    q = _as_f32(np.atleast_2d(queries))
+    n, nq = base.shape[0], q.shape[0]
+    limit = min(k, n)
+    l2 = metric == "l2"
+    best_v = np.full((nq, 0), 0.0)
+    best_i = np.full((nq, 0), 0, dtype=np.int64)
+    bn = (base.astype(np.float64) ** 2).sum(axis=1) if l2 else None
+    for qs in range(0, nq, query_block):
+        qb = q[qs:qs + query_block].astype(np.float64)
+        qn = (qb ** 2).sum(axis=1) if l2 else None
+        cur_v = np.empty((qb.shape[0], 0))
+        cur_i = np.empty((qb.shape[0], 0), dtype=np.int64)
+        for bs in range(0, n, base_block):
+            xb = base[bs:bs + base_block].astype(np.float64)
+            ip = qb @ xb.T
+            if l2:
+                key = np.maximum(qn[:, None] + bn[None, bs:bs + base_block] - 2.0 * ip, 0.0)
+            else:
+                key = -ip
+            v, i = _sorted_topk(key, min(limit, key.shape[1]))
+            cur_v = np.concatenate([cur_v, v], axis=1)
+            cur_i = np.concatenate([cur_i, i + bs], axis=1)
+            if cur_v.shape[1] > limit:
+                order = np.lexsort((cur_i, cur_v), axis=1)[:, :limit]
+                cur_v = np.take_along_axis(cur_v, order, axis=1)
+                cur_i = np.take_along_axis(cur_i, order, axis=1)
+        order = np.lexsort((cur_i, cur_v), axis=1)[:, :limit]
+        cur_v = np.take_along_axis(cur_v, order, axis=1)
+        cur_i = np.take_along_axis(cur_i, order, axis=1)
+        best_v = cur_v if qs == 0 else np.concatenate([best_v, cur_v], axis=0)
+        best_i = cur_i if qs == 0 else np.concatenate([best_i, cur_i], axis=0)
+    dist = best_v if l2 else -best_v
+    return _pad(dist, best_i, k, FLT_MAX if l2 else -FLT_MAX)
+
+
+def faiss_flat_search_blas(base: np.ndarray, queries: np.ndarray, k: int, metric: str = "l2",
+                           base_block: int = 131072, query_block: int = 4096) -> Tuple[np.ndarray, np.ndarray]:
+    """Speed-oriented variant of :func:`faiss_flat_search` used ONLY as ``bench.py``'s CPU
+    baseline: fp32 OpenBLAS sgemm per (query block x base block) + argpartition, all host
+    threads - the FAISS decomposition for nq >= 20 [FAISS-upstream]."""
+    base = _as_f32(base)
+    q = _as_f32(np.atleast_2d(queries))
+    n, nq = base.shape[0], q.shape[0]
+    limit = min(k, n)
+    l2 = metric == "l2"
+    bn = np.einsum("ij,ij->i", base, base) if l2 else None
+    out_v = np.empty((nq, limit), dtype=np.float32)
+    out_i = np.empty((nq, limit), dtype=np.int64)
+    for qs in range(0, nq, query_block):
+        qb = q[qs:qs + query_block]
+        qn = np.einsum("ij,ij->i", qb, qb) if l2 else None
+        vs, is_ = [], []
+        for bs in range(0, n, base_block):
+            ip = qb @ base[bs:bs + base_block].T
+            if l2:
+                ip *= -2.0
+                ip += bn[None, bs:bs + base_block]
+                ip += qn[:, None]
+                np.maximum(ip, 0.0, out=ip)
+            else:
+                np.negative(ip, out=ip)
+            kk = min(limit, ip.shape[1])
+            part = np.argpartition(ip, kk - 1, axis=1)[:, :kk] if kk < ip.shape[1] else \
+                np.broadcast_to(np.arange(ip.shape[1]), ip.shape)
+            vs.append(np.take_along_axis(ip, part, axis=1))
+            is_.append(part + bs)
+        v = np.concatenate(vs, axis=1)
+        i = np.concatenate(is_, axis=1)
+        order = np.argsort(v, axis=1, kind="stable")[:, :limit]
+        out_v[qs:qs + query_block] = np.take_along_axis(v, order, axis=1)
+        out_i[qs:qs + query_block] = np.take_along_axis(i, order, axis=1)
+    dist = out_v if l2 else -out_v
+    return _pad(dist, out_i, k, FLT_MAX if l2 else -FLT_MAX)
+
+
+# --------------------------------------------------------------------------- rerank (FAISS-LSH searcher)
+def candidate_budget(k: int, multiplier: float, max_candidates: Optional[int], num_db: int) -> int:
+    """Candidate count rule of ``FaissSearcher._batch_search_lsh_rerank``
+    (src/algorithms/modular.py:463-468)."""
+    c = max(k, 1)
+    if multiplier > 1.0:
+        c = int(max(c, k * multiplier))
+    if max_candidates is not None:
+        c = min(c, max_candidates)
+    return min(c, num_db)
+
+
+def rerank_search(base: np.ndarray, candidates: np.ndarray, queries: np.ndarray, k: int,
+                  metric: str = "l2") -> Tuple[np.ndarray, np.ndarray]:
+    """Exact re-scoring of per-query candidate ids (src/algorithms/modular.py:483-532).
+
+    ``candidates`` is [nq, C] int64 with -1 = invalid.  l2 -> sqrt of difference-form
+    squared distance; ip/cosine -> -score (cosine: ``base`` and ``queries`` already
+    normalised by the caller, modular.py:434-435,447-448).  Rows with fewer than k valid
+    candidates are padded with (+inf, -1) (modular.py:480-481).  A row with *no* valid
+    candidate falls back to the raw index order in the reference (modular.py:486-493);
+    here it stays fully padded - the CUDA path documents the same."""
+    base = _as_f32(base)
+    q = _as_f32(np.atleast_2d(queries))
+    nq = q.shape[0]
+    out_d = np.full((nq, k), np.inf, dtype=np.float32)
+    out_i = np.full((nq, k), -1, dtype=np.int64)
+    for r in range(nq):
+        valid = candidates[r][candidates[r] >= 0]
+        if valid.size == 0:
+            continue
+        vecs = base[valid]
+        if metric == "l2":
+            key = np.sum((vecs - q[r:r + 1]) ** 2, axis=1)
+        elif metric in ("ip", "cosine"):
+            key = -(q[r:r + 1] @ vecs.T).ravel()
+        else:
+            raise ValueError(f"Unsupported metric '{metric}'")
+        limit = min(k, key.shape[0])
+        order = np.lexsort((valid, key))[:limit]
+        vals = key[order]
+        out_d[r, :limit] = np.sqrt(vals) if metric == "l2" else vals
+        out_i[r, :limit] = valid[order]
+    return out_d, out_i
+
+
+# --------------------------------------------------------------------------- Python LSH (lsh.py)
+class LSHTables:
+    """Restatement of ``LSHIndexer.build`` (src/algorithms/lsh.py:95-138).
+
+    Draw order matters for reproducing the reference's buckets: one ``RandomState(seed)``,
+    first ``normal(size=(T, H, d))`` projections, then (l2 only) ``uniform(0, w, (T, H))``
+    offsets (lsh.py:70-76,99-101).  cosine keys: sign bits weighted ``1 << arange(H)`` into
+    a uint64 (lsh.py:78-80,102); l2 keys: tuple of ``floor((P v + b) / w)`` int32
+    (lsh.py:82-84)."""
+
+    def __init__(self, vectors: np.ndarray, metric: str, num_tables: int, hash_size: int,
+                 bucket_width: float, seed: int):
+        self.metric, self.T, self.H, self.w = metric, num_tables, hash_size, bucket_width
+        d = vectors.shape[1]
+        rng = np.random.RandomState(seed)
+        self.projections = rng.normal(size=(num_tables, hash_size, d)).astype(np.float32)
+        self.offsets = (rng.uniform(0.0, bucket_width, size=(num_tables, hash_size)).astype(np.float32)
+                        if metric == "l2" else None)
+        self.bit_weights = (1 << np.arange(hash_size, dtype=np.uint64))
+        store = vectors.astype(np.float32, copy=True)
+        if metric == "cosine":
+            store = safe_normalize(store)
+        self.vector_store = store
+        self.tables: List[Dict[object, List[int]]] = [defaultdict(list) for _ in range(num_tables)]
+        for idx in range(store.shape[0]):
+            for t, key in enumerate(self.hash(store[idx])):
+                self.tables[t][key].append(idx)
+
+    def hash(self, v: np.ndarray) -> List[object]:
+        keys: List[object] = []
+        for t in range(self.T):
+            proj = self.projections[t] @ v
+            if self.metric == "cosine":
+                bits = (proj >= 0).astype(np.uint64)
+                keys.append(int((bits * self.bit_weights).sum()))
+            else:
+                keys.append(tuple(np.floor((proj + self.offsets[t]) / self.w).astype(np.int32).tolist()))
+        return keys
+
+
+def lsh_candidates(tables: LSHTables, query: np.ndarray, k: int, candidate_multiplier: float,
+                   max_candidates: Optional[int], fallback_to_bruteforce: bool) -> np.ndarray:
+    """``LSHSearcher._gather_candidates`` + ``_select_candidates`` (lsh.py:219-240):
+    vote-count union of the T buckets in ``Counter.most_common()`` order (count descending,
+    first-seen order among equal counts), capped at ``max(k, ceil(mult*k))`` unless
+    ``max_candidates`` is given; no hit -> all rows (fallback) or nothing."""
+    votes: Counter = Counter()
+    for t, key in enumerate(tables.hash(query)):
+        bucket = tables.tables[t].get(key)
+        if bucket:
+            votes.update(bucket)
+    ordered = [i for i, _ in votes.most_common()]
+    if not ordered:
+        if fallback_to_bruteforce:
+            return np.arange(tables.vector_store.shape[0], dtype=np.int64)
+        return np.empty(0, dtype=np.int64)
+    cap = max_candidates if max_candidates is not None else max(k, int(math.ceil(candidate_multiplier * k)))
+    return np.asarray(ordered[:cap], dtype=np.int64)
+
+
+def lsh_search(tables: LSHTables, queries: np.ndarray, k: int, candidate_multiplier: float = 4.0,
+               max_candidates: Optional[int] = None, fallback_to_bruteforce: bool = True
+               ) -> Tuple[np.ndarray, np.ndarray]:
+    """``LSHSearcher.batch_search`` (lsh.py:252-298): per query, hash, gather, score with
+    cosine distance ``1 - v.q`` or Euclidean ``|v - q|`` (lsh.py:242-250), full argsort,
+    top-k, pad (+inf, -1)."""
+    q2 = np.atleast_2d(queries)
+    out_d = np.full((q2.shape[0], k), np.inf, dtype=np.float32)
+    out_i = np.full((q2.shape[0], k), -1, dtype=np.int64)
+    for r in range(q2.shape[0]):
+        q = q2[r].astype(np.float32, copy=True)
+        if tables.metric == "cosine":
+            nrm = np.linalg.norm(q)
+            q = np.zeros_like(q) if nrm == 0 else q / nrm
+        cand = lsh_candidates(tables, q, k, candidate_multiplier, max_candidates, fallback_to_bruteforce)
+        if cand.size == 0:
+            continue
+        vecs = tables.vector_store[cand]
+        if tables.metric == "cosine":
+            dist = (1.0 - vecs @ q).astype(np.float32)
+        else:
+            dist = np.linalg.norm(vecs - q[None, :], axis=1).astype(np.float32)
+        order = np.argsort(dist, kind="stable")[:k]
+        out_d[r, :order.size] = dist[order]
+        out_i[r, :order.size] = cand[order]
+    return out_d, out_i
+
+
+# --------------------------------------------------------------------------- IVF-Flat given centroids
+def ivf_assign(vectors: np.ndarray, centroids: np.ndarray, metric: str = "l2") -> np.ndarray:
+    """Nearest-centroid assignment used by ``IndexIVFFlat.add`` [FAISS-upstream]; the coarse
+    quantiser is flat L2 (l2) or flat inner product (ip / normalised cosine), reached from
+    src/algorithms/modular.py:279-283 and src/algorithms/approximate_search.py:39-47."""
+    _, idx = faiss_flat_search(centroids, vectors, 1, "l2" if metric == "l2" else "ip")
+    return idx[:, 0]
+
+
+def ivf_flat_search(base: np.ndarray, centroids: np.ndarray, assignments: np.ndarray,
+                    queries: np.ndarray, k: int, nprobe: int, metric: str = "l2"
+                    ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``IndexIVFFlat.search`` [FAISS-upstream] as called from ``FaissSearcher.batch_search``
+    (src/algorithms/modular.py:536-548): per query take the ``nprobe`` best centroids, scan
+    exactly those inverted lists, keep the k best.  Values follow the FAISS convention
+    (squared L2 ascending / raw IP descending, -1 / +-FLT_MAX padding); the wrapper class
+    negates for ip/cosine (modular.py:545-546).  Parity is defined *given identical
+    centroids and assignments* (FAISS k-means is not reproducible here).
+    Returns (D, I, probes)."""
+    base = _as_f32(base)
+    q = _as_f32(np.atleast_2d(queries))
+    l2 = metric == "l2"
+    nlist = centroids.shape[0]
+    nprobe = min(nprobe, nlist)
+    _, probes = faiss_flat_search(centroids, q, nprobe, "l2" if l2 else "ip")
+    order = np.argsort(assignments, kind="stable")
+    counts = np.bincount(assignments, minlength=nlist)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    out_d = np.full((q.shape[0], k), FLT_MAX if l2 else -FLT_MAX, dtype=np.float32)
+    out_i = np.full((q.shape[0], k), -1, dtype=np.int64)
+    b64 = base.astype(np.float64)
+    for r in range(q.shape[0]):
+        ids = np.concatenate([order[offsets[c]:offsets[c + 1]] for c in probes[r] if c >= 0])
+        if ids.size == 0:
+            continue
+        vec = b64[ids]
+        qq = q[r].astype(np.float64)
+        key = ((vec - qq) ** 2).sum(axis=1) if l2 else -(vec @ qq)
+        limit = min(k, ids.size)
+        sel = np.lexsort((ids, key))[:limit]
+        out_d[r, :limit] = key[sel] if l2 else -key[sel]
+        out_i[r, :limit] = ids[sel]
+    return out_d, out_i, probes
+
+
+# --------------------------------------------------------------------------- multi-shard merge
+def merge_topk(dists: Sequence[np.ndarray], ids: Sequence[np.ndarray], k: int,
+               ascending: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Merge per-shard sorted top-k lists into one; ties broken on (distance, id) so the
+    result is independent of the shard count.  id -1 entries are padding."""
+    d = np.concatenate(dists, axis=1).astype(np.float64)
+    i = np.concatenate(ids, axis=1)
+    key = d if ascending else -d
+    key = np.where(i < 0, np.inf, key)
+    order = np.lexsort((i, key), axis=1)[:, :k]
+    return (np.take_along_axis(np.concatenate(dists, axis=1), order, axis=1).astype(np.float32),
+            np.take_along_axis(i, order, axis=1).astype(np.int64))
+
+
+# --------------------------------------------------------------------------- metrics + comparator
+def recall_at_k(ground_truth: np.ndarray, predicted: np.ndarray, k: int) -> float:
+    """``recall_at_k`` (src/benchmark/metrics.py:4-34): mean over queries of
+    |gt[:k] & pred[:k]| / |gt[:k]| with k clipped to the predicted width."""
+    k = min(k, predicted.shape[1])
+    rec = np.zeros(ground_truth.shape[0])
+    for r in range(ground_truth.shape[0]):
+        gt = set(ground_truth[r, :k].tolist()) if ground_truth.shape[1] >= k else set(ground_truth[r].tolist())
+        pr = set(predicted[r, :k].tolist())
+        rec[r] = len(gt & pr) / len(gt) if gt else 0.0
+    return float(np.mean(rec))
+
+
+def compare_topk(ref_d: np.ndarray, ref_i: np.ndarray, got_d: np.ndarray, got_i: np.ndarray,
+                 rtol: float = 1e-5, atol: float = 0.0) -> Dict[str, object]:
+    """Tie-tolerant parity check (north star: "IDs bit-exact except where distances tie
+    within a stated 1e-5 relative tolerance, distances within that tolerance").
+
+    Position p of a row passes when got_i == ref_i, or when got_i[p] appears in the
+    reference row inside a run of reference distances that all lie within
+    ``rtol*|d| + atol`` of ref_d[p] (a tie group), or - at the tail - when got_d[p] is
+    within tolerance of the reference k-th distance (the boundary tie may pull in an id
+    the reference cut off).  Distances must match position-wise within tolerance.
+    Returns counts; ``ok`` is True when nothing fails."""
+    ref_d = np.asarray(ref_d, dtype=np.float64)
+    got_d = np.asarray(got_d, dtype=np.float64)
+    assert ref_d.shape == got_d.shape == ref_i.shape == got_i.shape, "shape mismatch"
+    finite = np.isfinite(ref_d) & np.isfinite(got_d)
+    tol = rtol * np.abs(ref_d) + atol
+    dist_bad = np.where(finite, np.abs(ref_d - got_d) > tol, ref_d != got_d)
+    # padding must agree exactly
+    dist_bad |= (ref_i < 0) != (got_i < 0)
+    id_exact = ref_i == got_i
+    id_bad = np.zeros_like(id_exact)
+    tie_swaps = 0
+    rows, cols = np.nonzero(~id_exact)
+    for r, c in zip(rows.tolist(), cols.tolist()):
+        t = tol[r, c]
+        pos = np.nonzero(ref_i[r] == got_i[r, c])[0]
+        if pos.size and abs(ref_d[r, pos[0]] - ref_d[r, c]) <= t:
+            tie_swaps += 1
+            continue
+        kth = ref_d[r, ref_i[r] >= 0][-1] if (ref_i[r] >= 0).any() else np.inf
+        if not pos.size and abs(got_d[r, c] - kth) <= rtol * abs(kth) + atol:
+            tie_swaps += 1
+            continue
+        id_bad[r, c] = True
+    return {
+        "ok": not dist_bad.any() and not id_bad.any(),
+        "n": int(ref_i.size),
+        "id_exact": int(id_exact.sum()),
+        "tie_swaps": int(tie_swaps),
+        "id_mismatch": int(id_bad.sum()),
+        "dist_mismatch": int(dist_bad.sum()),
+        "max_rel_err": float(np.max(np.where(finite & (np.abs(ref_d) > 0),
+                                             np.abs(ref_d - got_d) / np.maximum(np.abs(ref_d), 1e-30), 0.0),
+                                    initial=0.0)),
+    }
