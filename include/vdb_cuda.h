@@ -1,0 +1,148 @@
+/* libvdbcuda - C ABI of the B200 scan + top-k hot path.
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point replaces the arithmetic behind one reference call site
+ * (Human-Augment-Analytics/vectordb-retrieval, paths relative to the reference root):
+ *
+ *   vdb_flat_*       faiss.IndexFlat.add/search   src/algorithms/exact_search.py:38-39,58,78
+ *                    LinearSearcher.batch_search   src/algorithms/modular.py:336-387
+ *                    ground-truth flat search      src/benchmark/dataset.py:915-950
+ *   vdb_normalize_rows / vdb_row_norms
+ *                    _safe_normalize               src/algorithms/modular.py:109-111
+ *                    _normalize_rows               src/algorithms/lsh.py:13-16
+ *   vdb_ivf_*        index_factory("IVFn,Flat") train/add/search
+ *                                                  src/algorithms/modular.py:277-286,536-548
+ *                                                  src/algorithms/approximate_search.py:39-51,87
+ *   vdb_rerank_topk  FaissSearcher._batch_search_lsh_rerank  src/algorithms/modular.py:483-532
+ *                    LSHSearcher._compute_distances + argsort src/algorithms/lsh.py:242-283
+ *   vdb_merge_topk   (new) merge of per-GPU top-k lists after the NCCL allgather
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says host; row-major, `ld` in elements
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and allocates
+ *     nothing: the caller provides workspaces sized by the matching *_bytes() query
+ *   - return value: 0 = ok, non-zero = error; text via vdb_last_error() (thread-local)
+ *   - no C++ exception crosses this boundary
+ *   - distances out: float32; ids out: int64 (row index + id_offset), -1 = padding
+ */
+#ifndef VDB_CUDA_H_
+#define VDB_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDB_ABI_VERSION 1
+
+/* metric of the scoring kernels (cosine = IP on rows normalised by vdb_normalize_rows) */
+enum { VDB_METRIC_L2 = 0, VDB_METRIC_IP = 1 };
+
+/* output convention flags (the reference's classes disagree on these) */
+enum {
+  VDB_OUT_SQRT   = 1, /* L2: report sqrt(d2) (LinearSearcher, LSH rerank) instead of d2 (FAISS) */
+  VDB_OUT_NEGATE = 2, /* IP: report -score (LinearSearcher/FaissSearcher) instead of +score (raw FAISS) */
+  VDB_OUT_ONE_MINUS = 4 /* IP: report 1 - score (LSHSearcher cosine distance, lsh.py:246) */
+};
+
+/* which scan kernel vdb_flat_topk uses */
+enum { VDB_IMPL_AUTO = 0, VDB_IMPL_TCGEN05 = 1, VDB_IMPL_TCGEN05_1CTA = 2, VDB_IMPL_SIMT = 3 };
+
+const char* vdb_last_error(void);
+int vdb_abi_version(void);
+/* number of SMs of the current device (grid sizing / reporting) */
+int vdb_sm_count(int* out);
+
+/* ---- row utilities ------------------------------------------------------------------ */
+/* out[i] = sum_j x[i,j]^2 (fp64 accumulate, fp32 result) */
+int vdb_row_norms(const float* x, int64_t n, int d, int64_t ld, float* out, void* stream);
+/* y[i,:] = x[i,:] / |x[i,:]|, zero rows stay zero; y may alias x */
+int vdb_normalize_rows(const float* x, int64_t n, int d, int64_t ld, float* y, int64_t ld_y, void* stream);
+
+/* ---- flat (exact) index ------------------------------------------------------------- */
+/* Device layout of a prepared flat shard (all owned by the caller):
+ *   hi, lo : [n_pad, kpad] fp32, kpad = round_up(d, 32), n_pad = round_up(n, 256);
+ *            hi = x rounded to TF32, lo = x - hi (exact), so hi + lo == x bit-exactly;
+ *            padding rows / columns are zero.  These are the TMA / tcgen05 operands.
+ *   norms  : [n_pad] fp32, |x|^2 for L2, 0 for IP, +inf for padding rows.            */
+int     vdb_flat_kpad(int d);
+int64_t vdb_flat_npad(int64_t n);
+int vdb_flat_prepare(const float* x, int64_t n, int d, int64_t ld, int metric,
+                     float* hi, float* lo, float* norms, void* stream);
+
+/* Split queries the same way: q_hi, q_lo are [nq_pad, kpad], nq_pad = round_up(nq, 256). */
+int64_t vdb_flat_nqpad(int64_t nq);
+int vdb_flat_prepare_queries(const float* q, int64_t nq, int d, int64_t ld,
+                             float* q_hi, float* q_lo, void* stream);
+
+/* Workspace for one vdb_flat_topk call (pools of threshold-passing candidates, counters,
+ * per-query shared thresholds).  Depends on nq, k and the SM count only - never on n. */
+size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k);
+
+/* Fused scoring + selection + exact re-scoring of the winners.
+ *   keys   n_j - 2 q.x_j (L2) / -2 q.x_j (IP) from a 3xTF32 tcgen05 contraction (or the SIMT
+ *          kernel), filtered against a per-query running k'-th bound inside the epilogue;
+ *          the nq x n matrix is never written.
+ *   finish the k' >= k + 8 survivors are re-scored exactly (fp64 accumulate over hi+lo, the
+ *          difference form for L2), sorted by (distance, id) and the best k written.
+ *   out_d [nq,k] float32, out_i [nq,k] int64 = row + id_offset; rows beyond n: pad_value / -1.
+ *   flags  VDB_OUT_*; impl VDB_IMPL_*.  1 <= k <= 504.                                 */
+int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms,
+                  int64_t n, int d, int64_t id_offset,
+                  const float* q_hi, const float* q_lo, int64_t nq,
+                  int k, int flags, float pad_value, int impl,
+                  float* out_d, int64_t* out_i,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug / test hook: dense key matrix of the tcgen05 contraction for a small problem,
+ * keys [nq_pad, n_pad] fp32 (n_pad, nq_pad as above).  impl: VDB_IMPL_TCGEN05 / _1CTA / SIMT. */
+int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, int64_t n, int d,
+                        const float* q_hi, const float* q_lo, int64_t nq, int impl,
+                        float* keys, void* stream);
+
+/* ---- multi-GPU merge ----------------------------------------------------------------- */
+/* d_all/i_all: [parts, nq, k] as written by an allgather of per-shard results (each sorted
+ * best-first by (distance, id), padding id -1).  Parts must arrive in ascending id-range order
+ * (row-sharded base, allgather in rank order): then the merge is on (distance, id) and the
+ * result does not depend on the number of parts.  `descending` for raw-IP (+score) lists. */
+int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t nq, int k,
+                   int descending, float pad_value, float* out_d, int64_t* out_i, void* stream);
+
+/* ---- candidate re-ranking (LSH) ------------------------------------------------------- */
+/* base [n,d] fp32 row-major (ld elements, ld % 4 == 0, 16-byte aligned), cand [nq,C] int64
+ * (-1 = invalid), q [nq,d].  Exact fp32-input / fp64-accumulate scoring, difference form
+ * for L2.  Rows with fewer than k valid candidates are padded (pad_value, -1). */
+int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld,
+                    const int64_t* cand, int64_t nq, int c, const float* q, int64_t ld_q,
+                    int k, int flags, float pad_value, float* out_d, int64_t* out_i, void* stream);
+
+/* ---- IVF-Flat -------------------------------------------------------------------------- */
+/* Inverted lists, device layout ("interleaved-32"): list l occupies blocks
+ * [blk_off[l], blk_off[l+1]) ; block b holds 32 vectors as float4 [d4][32 lanes]
+ * (d4 = ceil(d/4), component c of slot v at ((b*d4 + c/4)*32 + v)*4 + c%4), so a warp reads
+ * one 512-byte line per 4 dimensions with 128-bit loads.  list_ids: [n_blocks*32] int32 row
+ * index inside the shard, -1 = empty slot (caller pre-fills with -1, list_vecs with 0). */
+int vdb_ivf_d4(int d);
+/* counts[l] += number of rows assigned to list l (assign in [0,nlist); counts pre-zeroed) */
+int vdb_ivf_count(const int32_t* assign, int64_t n, int nlist, int32_t* counts, void* stream);
+/* scatter rows into the interleaved layout; blk_off [nlist+1] int32 (prefix sum of
+ * ceil(count/32)), cursor [nlist] int32 zeroed scratch.  Slot order inside a list is
+ * arbitrary; search results never depend on it (the scan orders by (distance, id)). */
+int vdb_ivf_fill(const float* x, int64_t n, int d, int64_t ld, const int32_t* assign,
+                 const int32_t* blk_off, int nlist, int32_t* cursor,
+                 float* list_vecs, int32_t* list_ids, void* stream);
+/* probes [nq,nprobe] int64 as written by vdb_flat_topk over the centroids (-1 = skip); scans
+ * those lists with exact scoring (fp32 difference, fp64 accumulation) and keeps the top k.
+ * out_i = row + id_offset.  scanned_rows (nullable, pre-zeroed): += scanned list lengths. */
+int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_ids,
+                      const int32_t* blk_off, int nlist, int d,
+                      const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq,
+                      int k, int flags, float pad_value, int64_t id_offset,
+                      float* out_d, int64_t* out_i, int64_t* scanned_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDB_CUDA_H_ */

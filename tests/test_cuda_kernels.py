@@ -1,0 +1,203 @@
+"""GPU parity tests of the CUDA kernels, called through the C ABI, against the CPU oracle.
+
+Tolerances (north star): ids bit-exact except inside distance ties within 1e-5 relative;
+distances within 1e-5 relative (inner-product scores additionally get an absolute floor of
+1e-5 * |q||x|, since a relative bound is meaningless around zero)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import oracle  # noqa: E402  (checker only)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from vectordb_retrieval_b200 import _lib, engine
+    _lib.load()
+    return engine
+
+
+def _data(n, d, nq, seed=0, scale=1.0):
+    rng = np.random.RandomState(seed)
+    return (rng.randn(n, d) * scale).astype(np.float32), (rng.randn(nq, d) * scale).astype(np.float32)
+
+
+def _keys_ref(base, q, metric):
+    b, qq = base.astype(np.float64), q.astype(np.float64)
+    ip = qq @ b.T
+    return (b ** 2).sum(1)[None, :] - 2 * ip if metric == "l2" else -2 * ip
+
+
+IMPLS = ["tcgen05", "tcgen05_1cta", "simt"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("n,d,nq", [(1000, 128, 200), (700, 50, 130), (520, 160, 300), (300, 32, 5)])
+def test_dense_keys_match_fp64(eng, impl, n, d, nq):
+    """The 3xTF32 contraction (hi*hi + hi*lo + lo*hi, fp32 accumulate) must be fp32-accurate."""
+    from vectordb_retrieval_b200 import _lib
+    base, q = _data(n, d, nq, seed=n + d)
+    for metric in ("l2", "ip"):
+        shard = eng.FlatShard(base, metric, "cuda")
+        keys = shard.dense_keys(torch.from_numpy(q).cuda(), _lib.IMPL_NAMES[impl]).cpu().numpy().astype(np.float64)
+        ref = _keys_ref(base, q, metric)
+        scale = np.abs(q).astype(np.float64) @ np.abs(base).astype(np.float64).T * 2 + 1.0
+        err = np.abs(keys - ref) / scale
+        assert err.max() < 2e-6, f"{impl} {metric} max scaled err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def _check(ref, got, rtol=1e-5, atol=0.0):
+    res = oracle.compare_topk(ref[0], ref[1], got[0], got[1], rtol=rtol, atol=atol)
+    assert res["ok"], res
+    return res
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 64, 300, 10), (20000, 128, 700, 100), (3000, 50, 64, 200), (4, 2, 2, 2)])
+def test_flat_topk_matches_faiss_flat_oracle(eng, impl, metric, n, d, nq, k):
+    from vectordb_retrieval_b200 import _lib
+    base, q = _data(n, d, nq, seed=7 * n + d)
+    shard = eng.FlatShard(base, metric, "cuda")
+    D, I = shard.search(torch.from_numpy(q).cuda(), k, 0, oracle.FLT_MAX if metric == "l2" else -oracle.FLT_MAX,
+                        _lib.IMPL_NAMES[impl])
+    ref = oracle.faiss_flat_search(base, q, k, metric)
+    atol = 0.0 if metric == "l2" else 1e-5 * float(np.linalg.norm(base, axis=1).max() * np.linalg.norm(q, axis=1).max())
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=atol)
+    assert I.dtype == torch.int64 and D.dtype == torch.float32
+    kk = min(k, n)
+    assert oracle.recall_at_k(ref[1][:, :kk], I.cpu().numpy()[:, :kk], kk) == 1.0
+
+
+def test_flat_topk_linear_searcher_conventions_and_padding(eng):
+    """sqrt-L2 / negated IP / cosine as LinearSearcher reports them, (+inf, -1) padding for k > n."""
+    from vectordb_retrieval_b200 import _lib
+    base, q = _data(600, 24, 50, seed=3)
+    base[17] = 0.0
+    for metric, flags in (("l2", _lib.OUT_SQRT), ("ip", _lib.OUT_NEGATE), ("cosine", _lib.OUT_NEGATE)):
+        shard = eng.FlatShard(base, metric, "cuda")
+        D, I = shard.search(torch.from_numpy(q.copy()).cuda(), 10, flags, float("inf"))
+        ref = oracle.linear_search(base, q, 10, metric)
+        _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if metric == "l2" else 2e-6 * (1 if metric == "cosine" else 150))
+    shard = eng.FlatShard(base[:6], "l2", "cuda")
+    D, I = shard.search(torch.from_numpy(q[:3]).cuda(), 8, _lib.OUT_SQRT, float("inf"))
+    ref = oracle.linear_search(base[:6], q[:3], 8, "l2")
+    np.testing.assert_array_equal(I.cpu().numpy(), ref[1])
+    assert np.isinf(D.cpu().numpy()[:, 6:]).all()
+
+
+def test_self_distance_is_zero(eng):
+    """Difference-form re-scoring: a query equal to a base row has distance exactly ~0
+    (reference tests/test_composite_algorithm.py:134,165 demand atol 1e-6)."""
+    from vectordb_retrieval_b200 import _lib
+    base, _ = _data(5000, 128, 1, seed=11, scale=10.0)
+    q = base[100:140].copy()
+    D, I = eng.FlatShard(base, "l2", "cuda").search(torch.from_numpy(q).cuda(), 5, _lib.OUT_SQRT, float("inf"))
+    np.testing.assert_array_equal(I.cpu().numpy()[:, 0], np.arange(100, 140))
+    np.testing.assert_allclose(D.cpu().numpy()[:, 0], 0.0, atol=1e-6)
+
+
+def test_integer_valued_data_with_exact_ties(eng):
+    """SIFT-like U{0..255} integer vectors and duplicated rows produce exact ties."""
+    rng = np.random.RandomState(5)
+    base = rng.randint(0, 256, size=(8000, 128)).astype(np.float32)
+    base[4000:4100] = base[:100]          # duplicates
+    q = rng.randint(0, 256, size=(200, 128)).astype(np.float32)
+    q[:20] = base[:20]
+    D, I = eng.FlatShard(base, "l2", "cuda").search(torch.from_numpy(q).cuda(), 100)
+    ref = oracle.faiss_flat_search(base, q, 100, "l2")
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
+    # deterministic tie-break: lowest id first
+    assert (I.cpu().numpy()[:20, 0] == np.arange(20)).all() and (I.cpu().numpy()[:20, 1] == np.arange(4000, 4020)).all()
+
+
+def test_id_offset_and_merge_is_shard_count_invariant(eng):
+    base, q = _data(9000, 64, 300, seed=9)
+    ref = oracle.faiss_flat_search(base, q, 50, "l2")
+    qd = torch.from_numpy(q).cuda()
+    for parts in (2, 3, 8):
+        bounds = np.linspace(0, 9000, parts + 1).astype(int)
+        ds, is_ = [], []
+        for p in range(parts):
+            sh = eng.FlatShard(base[bounds[p]:bounds[p + 1]], "l2", "cuda", id_offset=int(bounds[p]))
+            d, i = sh.search(qd.clone(), 50)
+            ds.append(d), is_.append(i)
+        D, I = eng.merge_topk(torch.stack(ds), torch.stack(is_))
+        np.testing.assert_array_equal(I.cpu().numpy(), ref[1])
+        _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
+    # descending (+IP) merge
+    ref = oracle.faiss_flat_search(base, q, 20, "ip")
+    ds, is_ = [], []
+    for p in range(2):
+        sh = eng.FlatShard(base[p * 4500:(p + 1) * 4500], "ip", "cuda", id_offset=p * 4500)
+        d, i = sh.search(qd.clone(), 20, 0, -oracle.FLT_MAX)
+        ds.append(d), is_.append(i)
+    D, I = eng.merge_topk(torch.stack(ds), torch.stack(is_), descending=True, pad_value=-oracle.FLT_MAX)
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=1e-3)
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_rerank_matches_reference_golden_and_oracle(eng, metric):
+    import os
+    from oracle.gen_golden import rerank_inputs
+    from vectordb_retrieval_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "faiss_lsh_rerank.npz"))
+    base, q, cand = rerank_inputs()
+    rr = eng.Reranker(base, metric, "cuda")
+    flags = _lib.OUT_SQRT if metric == "l2" else _lib.OUT_NEGATE
+    D, I = rr.search(torch.from_numpy(q.copy()).cuda(), torch.from_numpy(cand).cuda(), 10, flags)
+    np.testing.assert_array_equal(I.cpu().numpy(), g[f"{metric}_I"])
+    np.testing.assert_allclose(D.cpu().numpy(), g[f"{metric}_D"], rtol=1e-5, atol=2e-6)
+    # larger random case, d not a multiple of 4, many candidates
+    rng = np.random.RandomState(1)
+    base, q = _data(20000, 50, 64, seed=21)
+    cand = np.stack([rng.permutation(20000)[:1500] for _ in range(64)]).astype(np.int64)
+    cand[5, 100:] = -1
+    b, qq = (oracle.safe_normalize(base), oracle.safe_normalize(q)) if metric == "cosine" else (base, q)
+    ref = oracle.rerank_search(b, cand, qq, 100, metric)
+    D, I = eng.Reranker(base, metric, "cuda").search(torch.from_numpy(q.copy()).cuda(), torch.from_numpy(cand).cuda(), 100, flags)
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if metric == "l2" else 1e-5)
+    # one-minus convention of the Python LSH searcher (lsh.py:246)
+    if metric == "cosine":
+        D1, I1 = eng.Reranker(base, metric, "cuda").search(torch.from_numpy(q.copy()).cuda(), torch.from_numpy(cand).cuda(), 100, _lib.OUT_ONE_MINUS)
+        np.testing.assert_allclose(D1.cpu().numpy()[np.isfinite(ref[0])], 1.0 + ref[0][np.isfinite(ref[0])], atol=2e-6)
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_ivf_scan_matches_oracle_given_same_centroids(eng, metric):
+    base, q = _data(30000, 50, 200, seed=31)
+    rng = np.random.RandomState(2)
+    cent = base[rng.permutation(30000)[:64]].copy()
+    if metric == "cosine":
+        cent = oracle.safe_normalize(cent)
+    ivf = eng.IVFShard(base, cent, metric, "cuda")
+    b, qq = (oracle.safe_normalize(base), oracle.safe_normalize(q)) if metric == "cosine" else (base, q)
+    m = "l2" if metric == "l2" else "ip"
+    assign = oracle.ivf_assign(b, cent, m)
+    got_assign = ivf.assign.cpu().numpy()
+    assert (got_assign == assign).mean() > 0.9999   # fp ties between two centroids are the only freedom
+    assert int(ivf.counts.sum().item()) == 30000
+    for nprobe in (1, 8, 64):
+        scanned = torch.zeros(1, dtype=torch.int64, device="cuda")
+        D, I = ivf.search(torch.from_numpy(q.copy()).cuda(), 100, nprobe, 0,
+                          oracle.FLT_MAX if m == "l2" else -oracle.FLT_MAX, scanned)
+        ref_d, ref_i, probes = oracle.ivf_flat_search(b, cent, got_assign, qq, 100, nprobe, m)
+        _check((ref_d, ref_i), (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if m == "l2" else 1e-5)
+        counts = np.bincount(got_assign, minlength=64)
+        assert int(scanned.item()) == int(counts[ivf.last_probes.cpu().numpy()].sum())
+    # nprobe == nlist is exact search
+    ref = oracle.faiss_flat_search(b, qq, 100, m)
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if m == "l2" else 1e-5)
+
+
+def test_row_utilities(eng):
+    base, _ = _data(1000, 50, 1, seed=4)
+    base[3] = 0
+    x = torch.from_numpy(base).cuda()
+    np.testing.assert_allclose(eng.row_norms(x).cpu().numpy(), (base.astype(np.float64) ** 2).sum(1), rtol=1e-6)
+    y = eng.normalize_rows_(x.clone()).cpu().numpy()
+    np.testing.assert_allclose(y, oracle.safe_normalize(base), rtol=1e-6, atol=1e-7)
+    assert (y[3] == 0).all()

@@ -1,0 +1,183 @@
+// Shared device helpers: packed (key,row) candidates, warp-wide bitonic sort, candidate pools.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+#include "../../include/vdb_cuda.h"
+
+namespace vdb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+void set_error(const char* fmt, ...);
+#define VDB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::vdb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                       __LINE__);                                                         \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+#define VDB_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::vdb::set_error(__VA_ARGS__);    \
+      return 2;                         \
+    }                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Candidate encoding: one 64-bit word, high half = order-preserving image of the fp32 key,
+// low half = row index inside the shard.  Unsigned compare == (key, row) lexicographic compare,
+// which makes every selection deterministic and independent of how the base is sharded.
+constexpr uint64_t kEmpty = ~0ull;
+
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+__device__ __forceinline__ uint64_t pack_key(float key, uint32_t row) {
+  return (static_cast<uint64_t>(f2ord(key)) << 32) | row;
+}
+__device__ __forceinline__ float packed_key(uint64_t p) { return ord2f(static_cast<uint32_t>(p >> 32)); }
+__device__ __forceinline__ uint32_t packed_row(uint64_t p) { return static_cast<uint32_t>(p); }
+
+// k' (kept candidates) for a requested k: at least 8 spare slots so that a 1e-6-level error
+// of the 3xTF32 key cannot push a true top-k row out before the exact re-scoring.
+__host__ __device__ constexpr int keep_for_k(int k) {
+  return k + 8 <= 32 ? 32 : k + 8 <= 128 ? 128 : k + 8 <= 256 ? 256 : k + 8 <= 512 ? 512 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bitonic sort of 32*E packed words held by one warp, element i = e*32 + lane, ascending.
+template <int E>
+__device__ __forceinline__ void warp_sort(uint64_t (&v)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int je = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pe = e ^ je;
+          if (pe > e) {
+            const bool asc = ((e * 32) & k) == 0;
+            const uint64_t a = v[e], b = v[pe];
+            const bool sw = (a > b) == asc;
+            v[e] = sw ? b : a;
+            v[pe] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const bool asc = (((e * 32) | lane) & k) == 0;
+          const uint64_t a = v[e];
+          const uint64_t b = __shfl_xor_sync(0xffffffffu, a, j);
+          const bool keep_min = ((lane & j) == 0) == asc;
+          const uint64_t mn = a < b ? a : b, mx = a < b ? b : a;
+          v[e] = keep_min ? mn : mx;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-query candidate pool in global memory (L2 resident): CAP = 2*KP slots.  The owner
+// thread appends every key that beats its running bound `thr`; when fewer than 32 free slots
+// remain the whole warp sorts that pool, keeps the best KP and tightens `thr` to the KP-th
+// key - a valid bound because at least KP scanned rows are <= it.  Called with all 32 lanes.
+struct PoolState {
+  float thr;
+  int cnt;
+};
+
+// slow path, one copy per kernel: compacts the pool of every lane flagged in `need`
+template <int KP>
+__device__ __noinline__ PoolState pool_compact(unsigned need, float thr, int cnt, uint64_t* pool, int lane,
+                                               uint32_t* thr_shared) {
+  constexpr int CAP = 2 * KP;
+  constexpr int E = CAP / 32;
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    uint64_t* p = reinterpret_cast<uint64_t*>(
+        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(pool), src));
+    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    __syncwarp();
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      v[e] = i < c ? __ldcg(p + i) : kEmpty;
+    }
+    warp_sort<E>(v, lane);
+#pragma unroll
+    for (int e = 0; e < KP / 32; ++e) __stcg(p + e * 32 + lane, v[e]);
+    const uint32_t kth = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v[KP / 32 - 1] >> 32), 31);
+    if (lane == src) {
+      cnt = KP;
+      thr = fminf(thr, ord2f(kth));
+      if (thr_shared) atomicMin(thr_shared, kth);
+    }
+    __syncwarp();
+  }
+  return PoolState{thr, cnt};
+}
+
+template <int KP>
+__device__ __forceinline__ void pool_maintain(float& thr, int& cnt, uint64_t* pool, int lane,
+                                              uint32_t* thr_shared /* this lane's global bound, may be null */) {
+  const unsigned need = __ballot_sync(0xffffffffu, cnt > 2 * KP - 32);
+  if (need) {
+    const PoolState st = pool_compact<KP>(need, thr, cnt, pool, lane, thr_shared);
+    thr = st.thr;
+    cnt = st.cnt;
+  }
+}
+
+// merge step shared by the finalisers: v[0..E) (sorted best so far) with E fresh words -> best E
+template <int E>
+__device__ __noinline__ void warp_merge_keep(uint64_t* best /* [E] in local */, const uint64_t* fresh, int lane) {
+  uint64_t v[2 * E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { v[e] = best[e]; v[E + e] = fresh[e]; }
+  warp_sort<2 * E>(v, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = v[e];
+}
+
+template <int E>
+__device__ __noinline__ void warp_sort_noinline(uint64_t* v, int lane) {
+  uint64_t w[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) w[e] = v[e];
+  warp_sort<E>(w, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = w[e];
+}
+
+__device__ __forceinline__ float ld_volatile_thr(const uint32_t* p) {
+  uint32_t o;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(o) : "l"(p));
+  return ord2f(o);
+}
+
+}  // namespace vdb

@@ -1,0 +1,495 @@
+// Flat (exact) search: planning, the CUDA-core scan (checker / fallback shape coverage),
+// pool finalisation with exact re-scoring, shard merge, and the C entry points.
+//   reference call sites replaced: src/algorithms/exact_search.py:38-39,78 (faiss.IndexFlat),
+//   src/algorithms/modular.py:336-387 (LinearSearcher.batch_search)
+#include <algorithm>
+#include <cstdio>
+
+#include "flat_tc.cuh"
+
+namespace vdb {
+
+// --------------------------------------------------------------------------------------------
+// workspace layout: [thr u32 nq_pad][pool_cnt i32 nq_pad*S][pools u64 nq_pad*S*CAP]
+struct FlatPlan {
+  int cta_group;       // 0 = SIMT
+  int n_qtiles;
+  int n_tiles;
+  int tile_rows;
+  int n_chunks;
+  int tiles_per_chunk;
+  int slots;
+};
+
+static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves) {
+  int s_max = std::max(1, (slots * waves + n_qtiles - 1) / n_qtiles);
+  s_max = std::min(s_max, std::max(slots, 16));   // few query tiles: one chunk per slot is enough
+  s_max = std::min(s_max, std::max(1, n_tiles));
+  int best = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= s_max; ++s) {
+    const long items = static_cast<long>(n_qtiles) * s;
+    const long rounds = (items + slots - 1) / slots;
+    const double eff = static_cast<double>(items) / static_cast<double>(rounds * slots);
+    if (eff >= best_eff - 1e-9) { best_eff = std::max(eff, best_eff); best = s; }
+  }
+  return best;
+}
+
+static int max_chunks(int64_t nq, int sm) {
+  // upper bound of pick_chunks over every implementation (tile count unbounded)
+  const int qt128 = static_cast<int>((nq + 127) / 128), qt64 = static_cast<int>((nq + 63) / 64);
+  int a = std::max(1, (sm * 8 + qt128 - 1) / qt128);          // 1-CTA tcgen05 (slots = sm)
+  int b = std::max(1, (2 * sm * 8 + qt64 - 1) / qt64);        // SIMT (slots = 2*sm)
+  return std::min(std::max(a, b), 2 * sm) + 2;
+}
+
+static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
+  FlatPlan p{};
+  if (impl == VDB_IMPL_SIMT) {
+    p.cta_group = 0; p.tile_rows = 64; p.slots = 2 * sm;
+    p.n_qtiles = static_cast<int>((nq + 63) / 64);
+  } else {
+    p.cta_group = impl == VDB_IMPL_TCGEN05_1CTA ? 1 : 2;
+    p.tile_rows = 128 * p.cta_group; p.slots = sm / p.cta_group;
+    p.n_qtiles = static_cast<int>((nq + p.tile_rows - 1) / p.tile_rows);
+  }
+  p.n_tiles = static_cast<int>(n_pad / p.tile_rows);
+  const int s = pick_chunks(p.n_qtiles, p.n_tiles, p.slots, 8);
+  p.tiles_per_chunk = (p.n_tiles + s - 1) / s;
+  p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  return p;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// --------------------------------------------------------------------------------------------
+__global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nq_pad) thr[i] = f2ord(CUDART_INF_F);
+  if (i < n_cnt) pool_cnt[i] = 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// CUDA-core scan with the same key / pool / bound protocol as the tcgen05 kernel.  64 queries x
+// 64 base rows per step, fp32 FFMA on x = hi + lo (exact fp32 inputs).  Used as the on-device
+// checker for the tensor-core kernel and for debugging; correctness first.
+template <int KP>
+__global__ void __launch_bounds__(256)
+flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ b_lo,
+                      const float* __restrict__ q_hi, const float* __restrict__ q_lo, int kpad,
+                      const FlatScanParams P) {
+  constexpr int CAP = 2 * KP;
+  __shared__ float Qs[64][33];
+  __shared__ float Bs[64][33];
+  __shared__ float Ss[64][65];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int qt = blockIdx.x, chunk = blockIdx.y;
+  const int t0 = chunk * P.tiles_per_chunk;
+  const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
+  const int64_t q_row0 = static_cast<int64_t>(qt) * 64;
+
+  const int64_t q = q_row0 + tid;              // epilogue role: threads 0..63 own one query each
+  const bool epi = tid < 64;
+  const bool live = epi && q < P.nq;
+  uint64_t* pool = epi ? P.pools + (q * P.n_chunks + chunk) * CAP : nullptr;
+  uint32_t* thr_g = epi ? P.thr + q : nullptr;
+  int cnt = 0;
+  float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
+
+  for (int t = t0; t < t1; ++t) {
+    const int64_t b_row0 = static_cast<int64_t>(t) * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < kpad; k0 += 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * 256, r = idx >> 5, c = idx & 31;
+        const int64_t qo = (q_row0 + r) * kpad + k0 + c, bo = (b_row0 + r) * kpad + k0 + c;
+        Qs[r][c] = q_hi[qo] + q_lo[qo];
+        Bs[r][c] = b_hi[bo] + b_lo[bo];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = Qs[ty * 4 + i][kk]; b[i] = Bs[tx * 4 + i][kk]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ss[ty * 4 + i][tx * 4 + j] = acc[i][j];
+    __syncthreads();
+    if (epi) {   // warps 0 and 1, fully populated
+      if (live) thr = fminf(thr, ld_volatile_thr(thr_g));
+      for (int c = 0; c < 2; ++c) {
+        pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t row = static_cast<uint32_t>(b_row0) + c * 32 + i;
+          const float key = fmaf(-2.f, Ss[tid][c * 32 + i], __ldg(P.norms + row));
+          if (P.dense != nullptr && live) P.dense[q * P.dense_ld + row] = key;
+          if (key < thr) { pool[cnt] = pack_key(key, row); ++cnt; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (epi) P.pool_cnt[q * P.n_chunks + chunk] = cnt;
+}
+
+// --------------------------------------------------------------------------------------------
+// Finalisation: one warp per query.  Gathers the query's pools, keeps the KP smallest keys,
+// re-scores those rows exactly (fp32 inputs x = hi + lo, fp64 accumulation; difference form
+// for L2, like LinearSearcher), sorts by (distance, row) and writes the best k.
+template <int KP>
+__global__ void __launch_bounds__(128)
+flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __restrict__ b_lo, int kpad,
+                     int64_t n, int64_t id_offset, const float* __restrict__ q_hi, const float* __restrict__ q_lo,
+                     int64_t nq, int n_chunks, const uint64_t* __restrict__ pools, const int* __restrict__ pool_cnt,
+                     int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  constexpr int CAP = 2 * KP;
+  constexpr int E = KP / 32;
+  __shared__ uint64_t stage_all[4][KP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (q >= nq) return;
+  uint64_t* stage = stage_all[warp];
+
+  uint64_t best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = kEmpty;
+  int staged = 0;
+  auto flush = [&]() {
+    uint64_t fresh[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      fresh[e] = i < staged ? stage[i] : kEmpty;
+    }
+    warp_merge_keep<E>(best, fresh, lane);
+    staged = 0;
+    __syncwarp();
+  };
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int c = min(pool_cnt[q * n_chunks + chunk], CAP);
+    const uint64_t* p = pools + (q * n_chunks + chunk) * CAP;
+    for (int base = 0; base < c; base += 32) {
+      const int m = min(32, c - base);
+      if (lane < m) stage[staged + lane] = __ldcg(p + base + lane);
+      staged += m;
+      __syncwarp();
+      if (staged > KP - 32) flush();
+    }
+  }
+  if (staged > 0) flush();
+
+  // exact re-scoring, one candidate at a time, coalesced over the row
+  const float* qh = q_hi + q * kpad;
+  const float* ql = q_lo + q * kpad;
+  uint64_t exact[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    exact[e] = kEmpty;
+    for (int src = 0; src < 32; ++src) {
+      const uint64_t cand = __shfl_sync(0xffffffffu, best[e], src);
+      if (cand == kEmpty) break;               // sorted: nothing valid after the first empty slot
+      const uint32_t row = packed_row(cand);
+      const float* xh = b_hi + static_cast<int64_t>(row) * kpad;
+      const float* xl = b_lo + static_cast<int64_t>(row) * kpad;
+      double acc = 0.0;
+      for (int j = lane; j < kpad; j += 32) {
+        const float xb = xh[j] + xl[j];
+        const float xq = qh[j] + ql[j];
+        if (metric == VDB_METRIC_L2) {
+          const float df = xb - xq;
+          acc += static_cast<double>(df) * static_cast<double>(df);
+        } else {
+          acc += static_cast<double>(xq) * static_cast<double>(xb);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float key = metric == VDB_METRIC_L2 ? static_cast<float>(acc) : -static_cast<float>(acc);
+      if (lane == src) exact[e] = pack_key(key, row);
+    }
+  }
+  warp_sort_noinline<E>(exact, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int r = e * 32 + lane;
+    if (r < k) {
+      float dv = pad_value;
+      int64_t iv = -1;
+      if (exact[e] != kEmpty) {
+        const float key = packed_key(exact[e]);
+        iv = static_cast<int64_t>(packed_row(exact[e])) + id_offset;
+        if (metric == VDB_METRIC_L2) dv = (flags & VDB_OUT_SQRT) ? sqrtf(key) : key;
+        else dv = (flags & VDB_OUT_NEGATE) ? key : ((flags & VDB_OUT_ONE_MINUS) ? 1.f + key : -key);
+      }
+      out_d[q * k + r] = dv;
+      out_i[q * k + r] = iv;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Merge of per-shard sorted lists after the allgather: one warp per query, (distance, id) order.
+template <int KP>
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i_all, int parts, int64_t nq,
+                  int k, int descending, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  // Candidates are keyed (value, position) with position = part*k + rank.  Parts arrive in
+  // ascending id-range order (row-sharded base, allgather in rank order) and every part is
+  // already sorted by (value, id), so (value, position) order IS (value, id) order: the merged
+  // list does not depend on how many parts the base was split into.
+  constexpr int E = KP / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (q >= nq) return;
+  uint64_t best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = kEmpty;
+  const int total = parts * k;
+  for (int base = 0; base < total; base += KP) {
+    uint64_t fresh[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int pos = base + e * 32 + lane;
+      uint64_t w = kEmpty;
+      if (pos < total) {
+        const int p = pos / k, r = pos % k;
+        const int64_t off = (static_cast<int64_t>(p) * nq + q) * k + r;
+        if (i_all[off] >= 0) {
+          const float val = d_all[off];
+          w = pack_key(descending ? -val : val, static_cast<uint32_t>(pos));
+        }
+      }
+      fresh[e] = w;
+    }
+    warp_merge_keep<E>(best, fresh, lane);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int r = e * 32 + lane;
+    if (r < k) {
+      float dv = pad_value;
+      int64_t iv = -1;
+      if (best[e] != kEmpty) {
+        const int pos = static_cast<int>(packed_row(best[e]));
+        const int64_t off = (static_cast<int64_t>(pos / k) * nq + q) * k + pos % k;
+        dv = d_all[off];
+        iv = i_all[off];
+      }
+      out_d[q * k + r] = dv;
+      out_i[q * k + r] = iv;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_operand_map(CUtensorMap* map, const float* ptr, int64_t rows, int kpad) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VDB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    VDB_REQUIRE(sym != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kpad) * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VDB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld kpad=%d", (int)r, (long long)rows, kpad);
+  return 0;
+}
+
+template <int CG, bool ARES, int KP, bool DENSE>
+static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mbh, const CUtensorMap& mbl,
+                     const FlatScanParams& P, int sm, cudaStream_t stream) {
+  auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE>;
+  constexpr int smem = tc::smem_bytes<ARES>();
+  static bool configured[64] = {};
+  int dev = 0;
+  VDB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = true;
+  }
+  const int n_items = P.n_qtiles * P.n_chunks;
+  const int clusters = std::max(1, std::min(sm / CG, n_items));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mqh, mql, mbh, mbl, P));
+  return 0;
+}
+
+template <int KP>
+static int run_scan(int impl, const float* hi, const float* lo, int64_t n_pad, int kpad, const float* q_hi,
+                    const float* q_lo, int64_t nq_pad, const FlatPlan& plan, const FlatScanParams& P, int sm,
+                    cudaStream_t stream) {
+  if (plan.cta_group == 0) {
+    dim3 grid(plan.n_qtiles, plan.n_chunks);
+    flat_scan_simt_kernel<KP><<<grid, 256, 0, stream>>>(hi, lo, q_hi, q_lo, kpad, P);
+    VDB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  CUtensorMap mqh, mql, mbh, mbl;
+  if (make_operand_map(&mqh, q_hi, nq_pad, kpad) || make_operand_map(&mql, q_lo, nq_pad, kpad) ||
+      make_operand_map(&mbh, hi, n_pad, kpad) || make_operand_map(&mbl, lo, n_pad, kpad))
+    return 3;
+  const bool ares = P.kb <= tc::kMaxResidentKb;
+  if constexpr (KP == 32) {   // the dense-key test hook exists for the smallest pool size only
+    if (P.dense != nullptr) {
+      if (plan.cta_group == 2)
+        return ares ? launch_tc<2, true, KP, true>(mqh, mql, mbh, mbl, P, sm, stream)
+                    : launch_tc<2, false, KP, true>(mqh, mql, mbh, mbl, P, sm, stream);
+      return ares ? launch_tc<1, true, KP, true>(mqh, mql, mbh, mbl, P, sm, stream)
+                  : launch_tc<1, false, KP, true>(mqh, mql, mbh, mbl, P, sm, stream);
+    }
+  }
+  if (plan.cta_group == 2) {
+    return ares ? launch_tc<2, true, KP, false>(mqh, mql, mbh, mbl, P, sm, stream)
+                : launch_tc<2, false, KP, false>(mqh, mql, mbh, mbl, P, sm, stream);
+  }
+  return ares ? launch_tc<1, true, KP, false>(mqh, mql, mbh, mbl, P, sm, stream)
+              : launch_tc<1, false, KP, false>(mqh, mql, mbh, mbl, P, sm, stream);
+}
+
+template <int KP>
+static int flat_topk_impl(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,
+                          int64_t id_offset, const float* q_hi, const float* q_lo, int64_t nq, int k, int flags,
+                          float pad_value, int impl, float* out_d, int64_t* out_i, void* ws, size_t ws_bytes,
+                          float* dense, cudaStream_t stream) {
+  int sm = 0;
+  if (vdb_sm_count(&sm)) return 1;
+  const int kpad = vdb_flat_kpad(d);
+  const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
+  const FlatPlan plan = make_plan(impl, nq, n_pad, sm);
+  constexpr int CAP = 2 * KP;
+  const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
+  const size_t off_pool = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_chunks * 4);
+  const size_t need = off_pool + static_cast<size_t>(nq_pad) * plan.n_chunks * CAP * 8;
+  VDB_REQUIRE(ws != nullptr && ws_bytes >= need, "vdb_flat_topk: workspace too small (%zu < %zu)", ws_bytes, need);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  FlatScanParams P{};
+  P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
+  P.n_chunks = plan.n_chunks; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.thr = reinterpret_cast<uint32_t*>(w);
+  P.pool_cnt = reinterpret_cast<int*>(w + off_cnt);
+  P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
+  P.dense = dense; P.dense_ld = n_pad;
+  const int64_t n_cnt = nq_pad * plan.n_chunks;
+  flat_init_kernel<<<static_cast<unsigned>((n_cnt + 255) / 256), 256, 0, stream>>>(P.thr, nq_pad, P.pool_cnt, n_cnt);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  const int rc = run_scan<KP>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, plan, P, sm, stream);
+  if (rc) return rc;
+  if (out_d != nullptr) {
+    flat_finalize_kernel<KP><<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
+        metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, plan.n_chunks, P.pools, P.pool_cnt, k, flags, pad_value,
+        out_d, out_i);
+    VDB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" {
+
+size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
+  int sm = 148;
+  vdb_sm_count(&sm);
+  const int kp = keep_for_k(k);
+  if (kp == 0 || nq <= 0) return 0;
+  const int64_t nq_pad = vdb_flat_nqpad(nq);
+  const int s = max_chunks(nq, sm);
+  return align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
+         static_cast<size_t>(nq_pad) * s * 2 * kp * 8 + 256;
+}
+
+int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,
+                  int64_t id_offset, const float* q_hi, const float* q_lo, int64_t nq, int k, int flags,
+                  float pad_value, int impl, float* out_d, int64_t* out_i, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "vdb_flat_topk: bad metric %d", metric);
+  VDB_REQUIRE(n > 0 && nq > 0 && d > 0, "vdb_flat_topk: empty problem n=%lld nq=%lld d=%d", (long long)n, (long long)nq, d);
+  VDB_REQUIRE(n < (int64_t(1) << 32), "vdb_flat_topk: shard too large (%lld rows; shard the base)", (long long)n);
+  const int kp = keep_for_k(k);
+  VDB_REQUIRE(k >= 1 && kp != 0, "vdb_flat_topk: k=%d unsupported (1..504)", k);
+  if (impl == VDB_IMPL_AUTO) impl = VDB_IMPL_TCGEN05;
+  VDB_REQUIRE(impl >= VDB_IMPL_TCGEN05 && impl <= VDB_IMPL_SIMT, "vdb_flat_topk: bad impl %d", impl);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define VDB_GO(KP)                                                                                              \
+  return flat_topk_impl<KP>(metric, hi, lo, norms, n, d, id_offset, q_hi, q_lo, nq, k, flags, pad_value, impl,  \
+                            out_d, out_i, workspace, workspace_bytes, nullptr, s)
+  switch (kp) {
+    case 32: VDB_GO(32);
+    case 128: VDB_GO(128);
+    case 256: VDB_GO(256);
+    default: VDB_GO(512);
+  }
+#undef VDB_GO
+}
+
+int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, int64_t n, int d, const float* q_hi,
+                        const float* q_lo, int64_t nq, int impl, float* keys, void* stream) {
+  VDB_REQUIRE(n > 0 && nq > 0 && d > 0, "vdb_flat_dense_keys: empty problem");
+  if (impl == VDB_IMPL_AUTO) impl = VDB_IMPL_TCGEN05;
+  const size_t bytes = vdb_flat_topk_workspace_bytes(nq, 24);
+  void* ws = nullptr;
+  VDB_CHECK_CUDA(cudaMalloc(&ws, bytes));   // test hook only: the product path never allocates
+  const int rc = flat_topk_impl<32>(VDB_METRIC_L2, hi, lo, norms, n, d, 0, q_hi, q_lo, nq, 24, 0, 0.f, impl, nullptr,
+                                    nullptr, ws, bytes, keys, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(ws);
+  if (rc) return rc;
+  VDB_CHECK_CUDA(e);
+  return 0;
+}
+
+int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t nq, int k, int descending,
+                   float pad_value, float* out_d, int64_t* out_i, void* stream) {
+  VDB_REQUIRE(parts >= 1 && nq > 0 && k >= 1, "vdb_merge_topk: bad shape");
+  const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
+  VDB_REQUIRE(kp != 0, "vdb_merge_topk: k=%d unsupported (<= 512)", k);
+  VDB_REQUIRE(static_cast<int64_t>(parts) * k < (int64_t(1) << 31), "vdb_merge_topk: parts*k too large");
+  const unsigned blocks = static_cast<unsigned>((nq + 3) / 4);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (kp) {
+    case 32: merge_topk_kernel<32><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
+    case 128: merge_topk_kernel<128><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
+    case 256: merge_topk_kernel<256><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
+    default: merge_topk_kernel<512><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
+  }
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

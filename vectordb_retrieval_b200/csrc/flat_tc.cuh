@@ -1,0 +1,297 @@
+// Flat (exact) scan on tcgen05 tensor cores: query x base contraction in 3xTF32 with the
+// per-query running top-k' bound applied straight out of TMEM - the nq x n score matrix is
+// never written to memory.
+//
+// Replaces the arithmetic of faiss.IndexFlat.search (reference src/algorithms/exact_search.py:78)
+// and LinearSearcher.batch_search (reference src/algorithms/modular.py:336-387).
+//
+// One work item = (query tile, base chunk).  Per CTA: 128 queries = 128 TMEM lanes, so each
+// epilogue thread owns one query and sees that query's keys as a register stream.
+//   warp 0      TMA producer  : base tiles (hi, lo) -> 128B-swizzled smem ring
+//   warp 1      MMA issuer    : per 32-wide k-block  hi*hi + hi*lo + lo*hi  (kind::tf32, fp32 acc in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue      : tcgen05.ld 32 columns, key = |x|^2 - 2 q.x, compare against the
+//                               query's bound, append the rare survivors to the query's pool
+// kCtaGroup == 2: two CTAs of a cluster form one 256 x 256 UMMA (cta_group::2); each loads half
+// of every base tile, which halves L2->smem traffic per SM.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vdb {
+
+struct FlatScanParams {
+  const float* norms;   // [n_pad]: |x|^2 (L2) / 0 (IP) / +inf (padding rows)
+  int64_t nq;           // live queries
+  int n_tiles;          // base tiles of TILE_N rows
+  int tiles_per_chunk;  // base tiles per work item
+  int n_chunks;         // S
+  int n_qtiles;         // query tiles of 128*kCtaGroup rows
+  int kb;               // k-blocks of 32 (kpad / 32)
+  uint64_t* pools;      // [nq_pad][S][2*KP]
+  int* pool_cnt;        // [nq_pad][S]
+  uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
+  float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
+  int64_t dense_ld;
+};
+
+namespace tc {
+constexpr int kThreads = 256;
+constexpr int kStages = 3;
+constexpr int kBlockRows = 128;                      // rows per operand block (A or B half)
+constexpr int kBlockBytes = kBlockRows * 128;        // 16 KB: 128 rows x 32 fp32, SWIZZLE_128B
+constexpr int kMaxResidentKb = 4;                    // query tile stays in smem when kpad <= 128
+constexpr int kNormStageBytes = 4 * 2 * 32 * 4;      // per epilogue warp, double buffered
+constexpr int kBarrierBytes = 256;
+
+template <bool kAResident>
+constexpr int smem_bytes() {
+  // resident: A_hi/A_lo [4] + ring of {B_hi, B_lo};  streamed: ring of {A_hi, A_lo, B_hi, B_lo}
+  return (kAResident ? 2 * kMaxResidentKb * kBlockBytes + kStages * 2 * kBlockBytes
+                     : kStages * 4 * kBlockBytes) +
+         kNormStageBytes + kBarrierBytes + 1024 /* manual 1024-byte alignment slack */;
+}
+}  // namespace tc
+
+template <int kCtaGroup, bool kAResident, int KP, bool kDense = false>
+__global__ void __launch_bounds__(tc::kThreads, 1)
+flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    const FlatScanParams P) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_SPECIFIC__)
+  using namespace ptx;
+  constexpr int UMMA_M = 128 * kCtaGroup;
+  constexpr int UMMA_N = 128 * kCtaGroup;     // base rows per tile (each CTA loads 128 of them)
+  constexpr int TMEM_COLS = 2 * UMMA_N;       // double-buffered accumulator
+  constexpr int CAP = 2 * KP;
+  constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // align inside the shared window (pointer arithmetic on the array keeps LDS/STS addressing)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // operand blocks
+  uint8_t* a_res = smem;                                                        // [2][kMaxResidentKb][16K] (hi, lo)
+  uint8_t* ring = smem + (kAResident ? 2 * tc::kMaxResidentKb * tc::kBlockBytes : 0);
+  constexpr int kStageBytes = (kAResident ? 2 : 4) * tc::kBlockBytes;
+  float* norm_stage = reinterpret_cast<float*>(ring + tc::kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(norm_stage) + tc::kNormStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's are used)
+  uint64_t* empty_bar = bars + tc::kStages;        // [kStages]  MMA -> TMA          (every CTA)
+  uint64_t* a_full_bar = bars + 2 * tc::kStages;   //            resident A landed   (leader)
+  uint64_t* a_empty_bar = a_full_bar + 1;          //            resident A consumed (every CTA)
+  uint64_t* tmem_full_bar = a_empty_bar + 1;       // [2]        MMA -> epilogue     (every CTA)
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]        epilogue -> MMA     (leader)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtaGroup == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x / kCtaGroup;
+  const int n_clusters = gridDim.x / kCtaGroup;
+  const int n_items = P.n_qtiles * P.n_chunks;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&map_q_hi); prefetch_tensormap(&map_q_lo);
+    prefetch_tensormap(&map_b_hi); prefetch_tensormap(&map_b_lo);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < tc::kStages; ++s) { mbar_init(full_bar + s, kCtaGroup); mbar_init(empty_bar + s, 1); }
+    mbar_init(a_full_bar, kCtaGroup);
+    mbar_init(a_empty_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar + b, 1); mbar_init(tmem_empty_bar + b, 4 * kCtaGroup); }
+    fence_barrier_init();
+  }
+  if (kCtaGroup == 2) cluster_sync_all();   // peer barriers must exist before any remote arrive
+  if (warp == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0; int item_iter = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_iter) {
+        const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+        const int t0 = chunk * P.tiles_per_chunk;
+        const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
+        const int q_row0 = (qt * kCtaGroup + cta_rank) * 128;
+        if (kAResident) {
+          if (item_iter > 0) mbar_wait(a_empty_bar, (item_iter - 1) & 1);
+          for (int kbi = 0; kbi < P.kb; ++kbi) {
+            tma_load_2d<kCtaGroup>(a_res + kbi * tc::kBlockBytes, &map_q_hi, a_full_bar, kbi * 32, q_row0);
+            tma_load_2d<kCtaGroup>(a_res + (tc::kMaxResidentKb + kbi) * tc::kBlockBytes, &map_q_lo, a_full_bar, kbi * 32, q_row0);
+          }
+          if (is_leader) mbar_arrive_expect_tx(a_full_bar, kCtaGroup * P.kb * 2 * tc::kBlockBytes);
+          else mbar_arrive_cluster(a_full_bar, 0);
+        }
+        for (int t = t0; t < t1; ++t) {
+          const int b_row0 = t * UMMA_N + cta_rank * 128;
+          for (int kbi = 0; kbi < P.kb; ++kbi) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* st = ring + stage * kStageBytes;
+            if (!kAResident) {
+              tma_load_2d<kCtaGroup>(st + 2 * tc::kBlockBytes, &map_q_hi, full_bar + stage, kbi * 32, q_row0);
+              tma_load_2d<kCtaGroup>(st + 3 * tc::kBlockBytes, &map_q_lo, full_bar + stage, kbi * 32, q_row0);
+            }
+            tma_load_2d<kCtaGroup>(st, &map_b_hi, full_bar + stage, kbi * 32, b_row0);
+            tma_load_2d<kCtaGroup>(st + tc::kBlockBytes, &map_b_lo, full_bar + stage, kbi * 32, b_row0);
+            if (is_leader) mbar_arrive_expect_tx(full_bar + stage, kCtaGroup * kStageBytes);
+            else mbar_arrive_cluster(full_bar + stage, 0);
+            if (++stage == tc::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA) ==========================
+    if (is_leader) {
+      int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_iter) {
+        const int chunk = item / P.n_qtiles;
+        const int t0 = chunk * P.tiles_per_chunk;
+        const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
+        if (kAResident) { mbar_wait(a_full_bar, item_iter & 1); tc_fence_after(); }
+        for (int t = t0; t < t1; ++t, ++tile_iter) {
+          const uint32_t buf = tile_iter & 1;
+          mbar_wait(tmem_empty_bar + buf, ((tile_iter >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * UMMA_N;
+          for (int kbi = 0; kbi < P.kb; ++kbi) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint8_t* st = ring + stage * kStageBytes;
+              const uint32_t b_hi = smem_u32(st), b_lo = smem_u32(st + tc::kBlockBytes);
+              const uint32_t a_hi = kAResident ? smem_u32(a_res + kbi * tc::kBlockBytes) : smem_u32(st + 2 * tc::kBlockBytes);
+              const uint32_t a_lo = kAResident ? smem_u32(a_res + (tc::kMaxResidentKb + kbi) * tc::kBlockBytes)
+                                               : smem_u32(st + 3 * tc::kBlockBytes);
+              const uint64_t da_hi = make_sw128_kmajor_desc(a_hi), da_lo = make_sw128_kmajor_desc(a_lo);
+              const uint64_t db_hi = make_sw128_kmajor_desc(b_hi), db_lo = make_sw128_kmajor_desc(b_lo);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)   // 4 x K=8 per 32-wide block: +32 bytes inside the swizzle atom
+                umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC, (kbi | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_lo + 2 * k, db_hi + 2 * k, IDESC, 1);
+              umma_commit<kCtaGroup>(empty_bar + stage);
+              if (kbi == P.kb - 1) umma_commit<kCtaGroup>(tmem_full_bar + buf);
+            }
+            __syncwarp();
+            if (++stage == tc::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (kAResident && elect_one()) umma_commit<kCtaGroup>(a_empty_bar);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue: filter keys against the running bound ==
+    const int ew = warp - 4;                       // TMEM lane quarter == warp % 4
+    float* nst = norm_stage + ew * 64;
+    constexpr int NCH = UMMA_N / 32;               // 32-column chunks per tile
+    uint32_t tile_iter = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+      const int t0 = chunk * P.tiles_per_chunk;
+      const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
+      const int64_t q = static_cast<int64_t>(qt * kCtaGroup + cta_rank) * 128 + ew * 32 + lane;
+      const bool live = q < P.nq;
+      uint64_t* pool = P.pools + (q * P.n_chunks + chunk) * CAP;
+      uint32_t* thr_g = P.thr + q;
+      int cnt = 0;
+      float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
+      // norms of the tile, lane l holds columns l, l+32, ...; fetched one tile ahead
+      float nrm_next[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) nrm_next[c] = __ldg(P.norms + static_cast<int64_t>(t0) * UMMA_N + c * 32 + lane);
+      for (int t = t0; t < t1; ++t, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1;
+        float nrm[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nrm[c] = nrm_next[c];
+        // loads whose latency hides behind this tile: the shared bound and the next tile's norms
+        const float thr_seen = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
+        if (t + 1 < t1) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) nrm_next[c] = __ldg(P.norms + static_cast<int64_t>(t + 1) * UMMA_N + c * 32 + lane);
+        }
+        mbar_wait(tmem_full_bar + buf, (tile_iter >> 1) & 1);
+        tc_fence_after();
+        const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * UMMA_N;
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+
+        auto consume = [&](const uint32_t (&v)[32], int c) {
+          float* ns = nst + (c & 1) * 32;
+          ns[lane] = nrm[c];
+          __syncwarp();
+          const uint32_t rbase = row0 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 n4 = *reinterpret_cast<const float4*>(ns + g * 4);
+            const float k0 = fmaf(-2.f, __uint_as_float(v[g * 4 + 0]), n4.x);
+            const float k1 = fmaf(-2.f, __uint_as_float(v[g * 4 + 1]), n4.y);
+            const float k2 = fmaf(-2.f, __uint_as_float(v[g * 4 + 2]), n4.z);
+            const float k3 = fmaf(-2.f, __uint_as_float(v[g * 4 + 3]), n4.w);
+            if (kDense) {
+              if (live) {
+                float* dp = P.dense + q * P.dense_ld + rbase + g * 4;
+                dp[0] = k0; dp[1] = k1; dp[2] = k2; dp[3] = k3;
+              }
+            }
+            if (fminf(fminf(k0, k1), fminf(k2, k3)) < thr) {     // rare: some key beats the bound
+              if (k0 < thr) { pool[cnt] = pack_key(k0, rbase + g * 4 + 0); ++cnt; }
+              if (k1 < thr) { pool[cnt] = pack_key(k1, rbase + g * 4 + 1); ++cnt; }
+              if (k2 < thr) { pool[cnt] = pack_key(k2, rbase + g * 4 + 2); ++cnt; }
+              if (k3 < thr) { pool[cnt] = pack_key(k3, rbase + g * 4 + 3); ++cnt; }
+            }
+          }
+        };
+
+#pragma unroll
+        for (int c = 0; c < NCH; c += 2) {
+          // chunk c is in flight in va: wait, start chunk c+1 into vb, then filter va under its latency
+          tmem_ld_wait();
+          tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+          pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
+          consume(va, c);
+          tmem_ld_wait();
+          if (c + 2 < NCH) {
+            tmem_ld_32x32(taddr + (c + 2) * 32, va);
+          } else {
+            // every column of this accumulator is in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (is_leader) mbar_arrive(tmem_empty_bar + buf);
+              else mbar_arrive_cluster(tmem_empty_bar + buf, 0);
+            }
+          }
+          pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
+          consume(vb, c + 1);
+        }
+        thr = fminf(thr, thr_seen);
+      }
+      P.pool_cnt[q * P.n_chunks + chunk] = cnt;
+    }
+  }
+
+  // ===================================== teardown ===========================================
+  tc_fence_before();
+  if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, TMEM_COLS);
+#else
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("vdb: flat_scan_tc_kernel needs sm_100a\n");
+  __trap();
+#endif
+}
+
+}  // namespace vdb

@@ -1,0 +1,156 @@
+// IVF-Flat: inverted-list construction and the list-scan + top-k kernel.
+//   reference: faiss.index_factory("IVF<n>,Flat") add/search reached from
+//   src/algorithms/modular.py:277-286,536-548 and src/algorithms/approximate_search.py:39-51,87
+// Coarse assignment (nearest / top-nprobe centroids) is vdb_flat_topk with base := centroids.
+//
+// List layout "interleaved-32": block = 32 vectors stored as float4 [d4][32]; a warp reads one
+// 512-byte line per 4 dimensions with 128-bit loads, one vector per lane, no cross-lane
+// reduction.  HBM-bound: algorithmic bytes = scanned rows * d * 4.
+#include "select.cuh"
+
+namespace vdb {
+
+__global__ void ivf_count_kernel(const int32_t* __restrict__ assign, int64_t n, int nlist, int32_t* counts) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int l = assign[i];
+    if (l >= 0 && l < nlist) atomicAdd(counts + l, 1);
+  }
+}
+
+// one warp per row; slot order inside a list is arbitrary (results never depend on it: the
+// scan orders by (distance, id))
+__global__ void ivf_fill_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, const int32_t* __restrict__ assign,
+                                const int32_t* __restrict__ blk_off, int nlist, int32_t* cursor, float* __restrict__ vecs,
+                                int32_t* __restrict__ ids) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const int l = assign[row];
+  if (l < 0 || l >= nlist) return;
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(cursor + l, 1);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  const int64_t b = blk_off[l] + (slot >> 5);
+  const int v = slot & 31;
+  const int d4 = (d + 3) / 4;
+  for (int c = lane; c < d4 * 4; c += 32)
+    vecs[((b * d4 + (c >> 2)) * 32 + v) * 4 + (c & 3)] = c < d ? x[row * ld + c] : 0.f;
+  if (lane == 0) ids[b * 32 + v] = static_cast<int32_t>(row);
+}
+
+template <int KP, int W>
+__global__ void __launch_bounds__(W * 32)
+ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __restrict__ ids,
+                const int32_t* __restrict__ blk_off, int nlist, int d4, const int64_t* __restrict__ probes, int nprobe,
+                const float* __restrict__ qmat, int64_t ld_q, int d, int k, int flags, float pad_value, int64_t id_offset,
+                float* __restrict__ out_d, int64_t* __restrict__ out_i, unsigned long long* scanned) {
+  constexpr int CAP = 2 * KP;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
+  int* cnts = reinterpret_cast<int*>(pools + W * CAP);
+  float4* qs = reinterpret_cast<float4*>(cnts + W);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = blockIdx.x;
+  for (int j = threadIdx.x; j < d4 * 4; j += W * 32) reinterpret_cast<float*>(qs)[j] = j < d ? qmat[q * ld_q + j] : 0.f;
+  __syncthreads();
+  WarpTopK<KP> sel;
+  sel.init(pools + warp * CAP);
+  unsigned rows_seen = 0;
+  int turn = 0;   // blocks of all probed lists are dealt round-robin to the W warps
+  for (int pi = 0; pi < nprobe; ++pi) {
+    const int64_t l = probes[q * nprobe + pi];
+    if (l < 0 || l >= nlist) continue;
+    const int b0 = blk_off[l], b1 = blk_off[l + 1];
+    int b = b0 + ((warp - turn) % W + W) % W;
+    turn = (turn + (b1 - b0)) % W;
+    for (; b < b1; b += W) {
+      const int id = ids[static_cast<int64_t>(b) * 32 + lane];
+      const float4* p = vecs + static_cast<int64_t>(b) * d4 * 32 + lane;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int c = 0; c < d4; ++c) {
+        const float4 x = __ldg(p + c * 32);
+        const float4 y = qs[c];
+        if (metric == VDB_METRIC_L2) {
+          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+          acc += static_cast<double>(d0) * d0 + static_cast<double>(d1) * d1 +
+                 static_cast<double>(d2) * d2 + static_cast<double>(d3) * d3;
+        } else {
+          acc += static_cast<double>(x.x) * y.x + static_cast<double>(x.y) * y.y +
+                 static_cast<double>(x.z) * y.z + static_cast<double>(x.w) * y.w;
+        }
+      }
+      const bool valid = id >= 0;
+      rows_seen += __popc(__ballot_sync(0xffffffffu, valid));
+      const float key = metric == VDB_METRIC_L2 ? static_cast<float>(acc) : -static_cast<float>(acc);
+      sel.push(valid, key, static_cast<uint32_t>(id), lane);
+    }
+  }
+  if (scanned != nullptr && lane == 0 && rows_seen) atomicAdd(scanned, static_cast<unsigned long long>(rows_seen));
+  cta_write_topk<KP, W>(sel, pools, cnts, warp, lane, metric, k, flags, pad_value, id_offset, out_d + q * k, out_i + q * k);
+}
+
+template <int KP, int W>
+static int launch_scan(int metric, const float* vecs, const int32_t* ids, const int32_t* blk_off, int nlist, int d,
+                       const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k, int flags,
+                       float pad_value, int64_t id_offset, float* out_d, int64_t* out_i, int64_t* scanned,
+                       cudaStream_t stream) {
+  const int d4 = (d + 3) / 4;
+  const size_t smem = static_cast<size_t>(W) * 2 * KP * 8 + W * 4 + static_cast<size_t>(d4) * 16;
+  auto kern = ivf_scan_kernel<KP, W>;
+  if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(
+      metric, reinterpret_cast<const float4*>(vecs), ids, blk_off, nlist, d4, probes, nprobe, q, ld_q, d, k, flags,
+      pad_value, id_offset, out_d, out_i, reinterpret_cast<unsigned long long*>(scanned));
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" {
+
+int vdb_ivf_d4(int d) { return (d + 3) / 4; }
+
+int vdb_ivf_count(const int32_t* assign, int64_t n, int nlist, int32_t* counts, void* stream) {
+  VDB_REQUIRE(n > 0 && nlist > 0, "vdb_ivf_count: bad shape");
+  ivf_count_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(assign, n, nlist, counts);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vdb_ivf_fill(const float* x, int64_t n, int d, int64_t ld, const int32_t* assign, const int32_t* blk_off, int nlist,
+                 int32_t* cursor, float* list_vecs, int32_t* list_ids, void* stream) {
+  VDB_REQUIRE(n > 0 && n < (int64_t(1) << 31) && d > 0 && ld >= d && nlist > 0, "vdb_ivf_fill: bad shape");
+  ivf_fill_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, d, ld, assign, blk_off, nlist, cursor, list_vecs, list_ids);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_ids, const int32_t* blk_off, int nlist,
+                      int d, const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k,
+                      int flags, float pad_value, int64_t id_offset, float* out_d, int64_t* out_i,
+                      int64_t* scanned_rows, void* stream) {
+  VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "vdb_ivf_scan_topk: bad metric %d", metric);
+  VDB_REQUIRE(nq > 0 && d > 0 && nlist > 0 && nprobe >= 1 && ld_q >= d, "vdb_ivf_scan_topk: bad shape");
+  VDB_REQUIRE((reinterpret_cast<uintptr_t>(list_vecs) & 15) == 0, "vdb_ivf_scan_topk: list_vecs must be 16-byte aligned");
+  const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
+  VDB_REQUIRE(k >= 1 && kp != 0, "vdb_ivf_scan_topk: k=%d unsupported (1..512)", k);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define VDB_GO(KP, W)                                                                                              \
+  return launch_scan<KP, W>(metric, list_vecs, list_ids, blk_off, nlist, d, probes, nprobe, q, ld_q, nq, k, flags, \
+                            pad_value, id_offset, out_d, out_i, scanned_rows, s)
+  switch (kp) {
+    case 32: VDB_GO(32, 8);
+    case 128: VDB_GO(128, 8);
+    case 256: VDB_GO(256, 8);
+    default: VDB_GO(512, 4);
+  }
+#undef VDB_GO
+}
+
+}  // extern "C"

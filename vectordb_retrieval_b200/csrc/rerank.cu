@@ -1,0 +1,95 @@
+// Exact re-scoring of per-query candidate sets + top-k (LSH rerank).
+//   reference: FaissSearcher._batch_search_lsh_rerank  src/algorithms/modular.py:483-532
+//              LSHSearcher._compute_distances + argsort  src/algorithms/lsh.py:242-283
+// HBM/L2-bound random row gather: 8 lanes fetch one candidate row with 128-bit loads (a full
+// 128-byte line per step), 4 candidates per warp step; fp32 difference, fp64 accumulation.
+#include "select.cuh"
+
+namespace vdb {
+
+template <int KP, int W>
+__global__ void __launch_bounds__(W * 32)
+rerank_topk_kernel(int metric, const float* __restrict__ base, int64_t n, int dpad, int64_t ld,
+                   const int64_t* __restrict__ cand, int c, const float* __restrict__ qmat, int64_t ld_q,
+                   int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  constexpr int CAP = 2 * KP;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
+  int* cnts = reinterpret_cast<int*>(pools + W * CAP);
+  float* qs = reinterpret_cast<float*>(cnts + W);   // W is a multiple of 4: stays 16-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = blockIdx.x;
+  for (int j = threadIdx.x; j < dpad; j += W * 32) qs[j] = qmat[q * ld_q + j];
+  __syncthreads();
+  WarpTopK<KP> sel;
+  sel.init(pools + warp * CAP);
+  const int sub = lane >> 3, sl = lane & 7;
+  const int64_t* cq = cand + q * c;
+  for (int c0 = warp * 4; c0 < c; c0 += W * 4) {
+    const int ci = c0 + sub;
+    const int64_t id = ci < c ? cq[ci] : -1;
+    const bool valid = id >= 0 && id < n;
+    double acc = 0.0;
+    if (valid) {
+      const float* row = base + id * ld;
+      for (int j = sl * 4; j < dpad; j += 32) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(row + j));
+        const float4 y = *reinterpret_cast<const float4*>(qs + j);
+        if (metric == VDB_METRIC_L2) {
+          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+          acc += static_cast<double>(d0) * d0 + static_cast<double>(d1) * d1 +
+                 static_cast<double>(d2) * d2 + static_cast<double>(d3) * d3;
+        } else {
+          acc += static_cast<double>(x.x) * y.x + static_cast<double>(x.y) * y.y +
+                 static_cast<double>(x.z) * y.z + static_cast<double>(x.w) * y.w;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    const float key = metric == VDB_METRIC_L2 ? static_cast<float>(acc) : -static_cast<float>(acc);
+    sel.push(valid && sl == 0, key, static_cast<uint32_t>(id), lane);
+  }
+  cta_write_topk<KP, W>(sel, pools, cnts, warp, lane, metric, k, flags, pad_value, 0, out_d + q * k, out_i + q * k);
+}
+
+template <int KP, int W>
+static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int64_t ld, const int64_t* cand, int64_t nq,
+                         int c, const float* q, int64_t ld_q, int k, int flags, float pad_value, float* out_d,
+                         int64_t* out_i, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(W) * 2 * KP * 8 + W * 4 + static_cast<size_t>(dpad) * 4;
+  auto kern = rerank_topk_kernel<KP, W>;
+  if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, c, q, ld_q, k, flags,
+                                                             pad_value, out_d, out_i);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld, const int64_t* cand,
+                               int64_t nq, int c, const float* q, int64_t ld_q, int k, int flags, float pad_value,
+                               float* out_d, int64_t* out_i, void* stream) {
+  VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "vdb_rerank_topk: bad metric %d", metric);
+  VDB_REQUIRE(n > 0 && n < (int64_t(1) << 32) && nq > 0 && c >= 1 && d > 0, "vdb_rerank_topk: bad shape");
+  const int dpad = (d + 3) / 4 * 4;
+  VDB_REQUIRE(ld % 4 == 0 && ld >= dpad && ld_q % 4 == 0 && ld_q >= dpad,
+              "vdb_rerank_topk: rows must be zero-padded to a multiple of 4 floats (d=%d ld=%lld ld_q=%lld)", d,
+              (long long)ld, (long long)ld_q);
+  VDB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+              "vdb_rerank_topk: base/q must be 16-byte aligned");
+  VDB_REQUIRE(dpad <= 16384, "vdb_rerank_topk: d too large");
+  const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
+  VDB_REQUIRE(k >= 1 && kp != 0, "vdb_rerank_topk: k=%d unsupported (1..512)", k);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (kp) {
+    case 32: return launch_rerank<32, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
+    case 128: return launch_rerank<128, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
+    case 256: return launch_rerank<256, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
+    default: return launch_rerank<512, 4>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
+  }
+}

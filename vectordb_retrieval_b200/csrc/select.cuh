@@ -1,0 +1,95 @@
+// Warp-private running top-k' in shared memory, shared by the IVF list scan and the LSH rerank.
+#pragma once
+#include "common.cuh"
+
+namespace vdb {
+
+template <int KP>
+struct WarpTopK {
+  static constexpr int CAP = 2 * KP;
+  static constexpr int E = CAP / 32;
+  uint64_t* pool;   // CAP slots, warp-private shared memory
+  int cnt;          // warp-uniform
+  float thr;        // warp-uniform: KP-th smallest key seen so far (+inf until KP keys were seen)
+
+  __device__ __forceinline__ void init(uint64_t* p) { pool = p; cnt = 0; thr = CUDART_INF_F; }
+
+  // one out-of-line copy per kernel; state travels by value so the hot loop keeps it in registers
+  static __device__ __noinline__ PoolState compact_impl(uint64_t* pool, int cnt, float thr, int lane) {
+    __syncwarp();
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      v[e] = i < cnt ? pool[i] : kEmpty;
+    }
+    warp_sort<E>(v, lane);
+#pragma unroll
+    for (int e = 0; e < KP / 32; ++e) pool[e * 32 + lane] = v[e];
+    const uint64_t kth = __shfl_sync(0xffffffffu, v[KP / 32 - 1], 31);
+    if (kth != kEmpty) thr = fminf(thr, packed_key(kth));
+    __syncwarp();
+    return PoolState{thr, min(cnt, KP)};
+  }
+  __device__ __forceinline__ void compact(int lane) {
+    const PoolState st = compact_impl(pool, cnt, thr, lane);
+    thr = st.thr;
+    cnt = st.cnt;
+  }
+
+  // every lane of the warp calls; `valid` lanes offer one (key,row) each
+  __device__ __forceinline__ void push(bool valid, float key, uint32_t row, int lane) {
+    if (cnt > CAP - 32) compact(lane);
+    const bool pass = valid && key < thr;
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) pool[cnt + __popc(m & ((1u << lane) - 1u))] = pack_key(key, row);
+    cnt += __popc(m);
+  }
+};
+
+// Merge the W warp pools of a CTA (warp 0 does it) and write the best k as (distance, id).
+//   key -> distance: L2: key (or sqrt), IP: key = -score.
+template <int KP, int W>
+__device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* pools_smem, int* cnts_smem, int warp, int lane,
+                                               int metric, int k, int flags, float pad_value, int64_t id_offset,
+                                               float* out_d, int64_t* out_i) {
+  constexpr int CAP = 2 * KP;
+  constexpr int E = KP / 32;
+  if (lane == 0) cnts_smem[warp] = mine.cnt;
+  __syncthreads();
+  if (warp != 0) return;
+  uint64_t best[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) best[e] = kEmpty;
+  for (int w = 0; w < W; ++w) {
+    const int c = cnts_smem[w];
+    const uint64_t* p = pools_smem + w * CAP;
+    for (int base = 0; base < c; base += KP) {
+      uint64_t fresh[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + e * 32 + lane;
+        fresh[e] = i < c ? p[i] : kEmpty;
+      }
+      warp_merge_keep<E>(best, fresh, lane);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int r = e * 32 + lane;
+    if (r < k) {
+      float dv = pad_value;
+      int64_t iv = -1;
+      if (best[e] != kEmpty) {
+        const float key = packed_key(best[e]);
+        iv = static_cast<int64_t>(packed_row(best[e])) + id_offset;
+        if (metric == VDB_METRIC_L2) dv = (flags & VDB_OUT_SQRT) ? sqrtf(key) : key;
+        else dv = (flags & VDB_OUT_NEGATE) ? key : ((flags & VDB_OUT_ONE_MINUS) ? 1.f + key : -key);
+      }
+      out_d[r] = dv;
+      out_i[r] = iv;
+    }
+  }
+}
+
+}  // namespace vdb

@@ -1,0 +1,283 @@
+"""Device-side operators: torch owns memory and streams, libvdbcuda.so does the arithmetic.
+
+Everything here is plumbing around the C ABI (include/vdb_cuda.h): allocate, copy, call.
+No arithmetic of the hot path is done in torch, and nothing falls back to the CPU."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import METRIC_IP, METRIC_L2, check, ptr
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("vectordb_retrieval_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError(f"device must be a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def metric_code(metric: str) -> int:
+    return METRIC_L2 if metric == "l2" else METRIC_IP
+
+
+def to_device_f32(x, dev: torch.device, chunk_rows: int = 1 << 20) -> torch.Tensor:
+    """[n, d] float32 contiguous device tensor from numpy (any dtype/layout, memmap ok) or torch."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float32).contiguous()
+    x = np.asarray(x) if not isinstance(x, np.ndarray) else x
+    if x.ndim != 2:
+        raise RuntimeError(f"expected a 2-D array, got shape {x.shape}")
+    n, d = x.shape
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    for s in range(0, n, chunk_rows):
+        blk = np.ascontiguousarray(x[s:s + chunk_rows], dtype=np.float32)
+        out[s:s + blk.shape[0]].copy_(torch.from_numpy(blk), non_blocking=False)
+    return out
+
+
+def normalize_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place row normalisation on device (zero rows stay zero)."""
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        check(lib.vdb_normalize_rows(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(x), x.stride(0), _stream(x.device)),
+              "vdb_normalize_rows")
+    return x
+
+
+def row_norms(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.vdb_row_norms(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(out), _stream(x.device)), "vdb_row_norms")
+    return out
+
+
+class FlatShard:
+    """One GPU's row range of a flat (exact) index, in the tcgen05 operand layout.
+
+    HBM layout: ``hi``/``lo`` [n_pad, kpad] fp32 (TF32 split, hi + lo == x exactly) and
+    ``norms`` [n_pad]; the original fp32 rows are not kept (2x the base bytes in total)."""
+
+    def __init__(self, vectors, metric: str = "l2", device=None, id_offset: int = 0, upload_rows: int = 1 << 20):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.id_offset = int(id_offset)
+        n, d = int(vectors.shape[0]), int(vectors.shape[1])
+        if n <= 0:
+            raise RuntimeError("cannot build a flat index over zero vectors")
+        self.n, self.d = n, d
+        self.kpad = self.lib.vdb_flat_kpad(d)
+        self.n_pad = self.lib.vdb_flat_npad(n)
+        with torch.cuda.device(self.dev):
+            self.hi = torch.empty((self.n_pad, self.kpad), dtype=torch.float32, device=self.dev)
+            self.lo = torch.empty((self.n_pad, self.kpad), dtype=torch.float32, device=self.dev)
+            self.norms = torch.empty(self.n_pad, dtype=torch.float32, device=self.dev)
+            upload_rows = max(256, upload_rows // 256 * 256)
+            for s in range(0, n, upload_rows):
+                blk = to_device_f32(vectors[s:s + upload_rows], self.dev)
+                if metric == "cosine":
+                    normalize_rows_(blk)
+                m = blk.shape[0]
+                check(self.lib.vdb_flat_prepare(ptr(blk), m, d, blk.stride(0), metric_code(metric),
+                                                self.hi[s:].data_ptr(), self.lo[s:].data_ptr(), self.norms[s:].data_ptr(),
+                                                _stream(self.dev)), "vdb_flat_prepare")
+                del blk
+            torch.cuda.current_stream(self.dev).synchronize()
+        self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._qbuf: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def memory_bytes(self) -> int:
+        return (self.hi.numel() + self.lo.numel() + self.norms.numel()) * 4
+
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        key = (nq, k)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.vdb_flat_topk_workspace_bytes(nq, k)
+            if nbytes == 0:
+                raise RuntimeError(f"k={k} is not supported by the flat search (1..504)")
+            self._ws.clear()  # one live workspace per shard
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            self._ws[key] = ws
+        return ws
+
+    def _query_operands(self, nq: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        nq_pad = self.lib.vdb_flat_nqpad(nq)
+        buf = self._qbuf.get(nq_pad)
+        if buf is None:
+            self._qbuf.clear()
+            buf = (torch.empty((nq_pad, self.kpad), dtype=torch.float32, device=self.dev),
+                   torch.empty((nq_pad, self.kpad), dtype=torch.float32, device=self.dev))
+            self._qbuf[nq_pad] = buf
+        return buf
+
+    def prepare_queries(self, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q: [nq, d] fp32 device tensor (normalised in place for cosine)."""
+        if self.metric == "cosine":
+            normalize_rows_(q)
+        q_hi, q_lo = self._query_operands(q.shape[0])
+        check(self.lib.vdb_flat_prepare_queries(ptr(q), q.shape[0], self.d, q.stride(0), ptr(q_hi), ptr(q_lo),
+                                                _stream(self.dev)), "vdb_flat_prepare_queries")
+        return q_hi, q_lo
+
+    def search(self, q: torch.Tensor, k: int, flags: int = 0, pad_value: float = FLT_MAX, impl: int = _lib.IMPL_AUTO,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fused scan + top-k for a device query batch; returns device tensors (D [nq,k], I [nq,k])."""
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise RuntimeError(f"query shape {tuple(q.shape)} does not match dimension {self.d}")
+        nq = q.shape[0]
+        with torch.cuda.device(self.dev):
+            q_hi, q_lo = self.prepare_queries(q)
+            if out is None:
+                out = (torch.empty((nq, k), dtype=torch.float32, device=self.dev),
+                       torch.empty((nq, k), dtype=torch.int64, device=self.dev))
+            ws = self._workspace(nq, k)
+            check(self.lib.vdb_flat_topk(metric_code(self.metric), ptr(self.hi), ptr(self.lo), ptr(self.norms),
+                                         self.n, self.d, self.id_offset, ptr(q_hi), ptr(q_lo), nq, k, flags,
+                                         pad_value, impl, ptr(out[0]), ptr(out[1]), ptr(ws), ws.numel(),
+                                         _stream(self.dev)), "vdb_flat_topk")
+        return out
+
+    def dense_keys(self, q: torch.Tensor, impl: int) -> torch.Tensor:
+        """Test hook: the full key matrix n_j - 2 q.x_j as the scan kernel computes it."""
+        nq = q.shape[0]
+        with torch.cuda.device(self.dev):
+            q_hi, q_lo = self.prepare_queries(q)
+            keys = torch.zeros((self.lib.vdb_flat_nqpad(nq), self.n_pad), dtype=torch.float32, device=self.dev)
+            check(self.lib.vdb_flat_dense_keys(ptr(self.hi), ptr(self.lo), ptr(self.norms), self.n, self.d,
+                                               ptr(q_hi), ptr(q_lo), nq, impl, ptr(keys), _stream(self.dev)),
+                  "vdb_flat_dense_keys")
+        return keys[:nq, :self.n]
+
+
+def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, descending: bool = False, pad_value: float = FLT_MAX
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[parts, nq, k] gathered shard results -> merged [nq, k] (parts in ascending id order)."""
+    lib = _lib.load()
+    parts, nq, k = d_all.shape
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=d_all.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=d_all.device)
+    with torch.cuda.device(d_all.device):
+        check(lib.vdb_merge_topk(ptr(d_all), ptr(i_all), parts, nq, k, int(descending), pad_value, ptr(out_d), ptr(out_i),
+                                 _stream(d_all.device)), "vdb_merge_topk")
+    return out_d, out_i
+
+
+def pad_cols(x: torch.Tensor, multiple: int = 4) -> torch.Tensor:
+    """Zero-pad the row pitch to a multiple of `multiple` floats (16-byte aligned rows)."""
+    d = x.shape[1]
+    dp = (d + multiple - 1) // multiple * multiple
+    if dp == d and x.is_contiguous():
+        return x
+    out = torch.zeros((x.shape[0], dp), dtype=torch.float32, device=x.device)
+    out[:, :d].copy_(x)
+    return out
+
+
+class Reranker:
+    """Exact re-scoring of candidate ids against fp32 base rows kept on device (LSH rerank)."""
+
+    def __init__(self, vectors, metric: str = "l2", device=None):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        base = to_device_f32(vectors, self.dev)
+        if metric == "cosine":
+            normalize_rows_(base)
+        self.n, self.d = base.shape
+        self.base = pad_cols(base)
+
+    def memory_bytes(self) -> int:
+        return self.base.numel() * 4
+
+    def search(self, q: torch.Tensor, cand: torch.Tensor, k: int, flags: int, pad_value: float = math.inf
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        nq, c = cand.shape
+        with torch.cuda.device(self.dev):
+            if self.metric == "cosine":
+                normalize_rows_(q)
+            qp = pad_cols(q)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
+            check(self.lib.vdb_rerank_topk(metric_code(self.metric), ptr(self.base), self.n, self.d, self.base.stride(0),
+                                           ptr(cand), nq, c, ptr(qp), qp.stride(0), k, flags, pad_value,
+                                           ptr(out_d), ptr(out_i), _stream(self.dev)), "vdb_rerank_topk")
+        return out_d, out_i
+
+
+class IVFShard:
+    """IVF-Flat index of one GPU's rows: centroids as a FlatShard (coarse quantiser) plus the
+    inverted lists in the interleaved-32 layout."""
+
+    def __init__(self, vectors, centroids, metric: str = "l2", device=None, id_offset: int = 0,
+                 assign_batch: int = 1 << 18):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.id_offset = int(id_offset)
+        base = to_device_f32(vectors, self.dev)
+        if metric == "cosine":
+            normalize_rows_(base)
+        self.n, self.d = base.shape
+        cent = to_device_f32(centroids, self.dev)
+        self.nlist = cent.shape[0]
+        # coarse quantiser: flat L2 / flat IP over the centroids (cosine data is already normalised)
+        self.quantizer = FlatShard(cent, "l2" if metric == "l2" else "ip", self.dev)
+        self.centroids = cent
+        with torch.cuda.device(self.dev):
+            assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
+            for s in range(0, self.n, assign_batch):
+                _, idx = self.quantizer.search(base[s:s + assign_batch].clone(), 1)
+                assign[s:s + assign_batch] = idx[:, 0].to(torch.int32)
+            self.assign = assign
+            counts = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_ivf_count(ptr(assign), self.n, self.nlist, ptr(counts), _stream(self.dev)), "vdb_ivf_count")
+            blocks = (counts.to(torch.int64) + 31) // 32
+            blk_off = torch.zeros(self.nlist + 1, dtype=torch.int32, device=self.dev)
+            blk_off[1:] = torch.cumsum(blocks, 0).to(torch.int32)
+            n_blocks = int(blk_off[-1].item())
+            self.d4 = self.lib.vdb_ivf_d4(self.d)
+            self.list_vecs = torch.zeros(max(n_blocks, 1) * self.d4 * 32 * 4, dtype=torch.float32, device=self.dev)
+            self.list_ids = torch.full((max(n_blocks, 1) * 32,), -1, dtype=torch.int32, device=self.dev)
+            cursor = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_ivf_fill(ptr(base), self.n, self.d, base.stride(0), ptr(assign), ptr(blk_off), self.nlist,
+                                        ptr(cursor), ptr(self.list_vecs), ptr(self.list_ids), _stream(self.dev)),
+                  "vdb_ivf_fill")
+            self.blk_off, self.counts, self.n_blocks = blk_off, counts, n_blocks
+            torch.cuda.current_stream(self.dev).synchronize()
+
+    def memory_bytes(self) -> int:
+        return self.list_vecs.numel() * 4 + self.list_ids.numel() * 4 + self.quantizer.memory_bytes()
+
+    def search(self, q: torch.Tensor, k: int, nprobe: int, flags: int = 0, pad_value: float = FLT_MAX,
+               scanned: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        nq = q.shape[0]
+        nprobe = max(1, min(int(nprobe), self.nlist))
+        with torch.cuda.device(self.dev):
+            if self.metric == "cosine":
+                normalize_rows_(q)
+            _, probes = self.quantizer.search(q.clone(), nprobe)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
+            check(self.lib.vdb_ivf_scan_topk(metric_code(self.metric), ptr(self.list_vecs), ptr(self.list_ids),
+                                             ptr(self.blk_off), self.nlist, self.d, ptr(probes), nprobe, ptr(q),
+                                             q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
+                                             ptr(scanned), _stream(self.dev)), "vdb_ivf_scan_topk")
+        self.last_probes = probes
+        return out_d, out_i
