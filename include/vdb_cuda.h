@@ -72,7 +72,9 @@ int64_t vdb_flat_npad(int64_t n);
 int vdb_flat_prepare(const float* x, int64_t n, int d, int64_t ld, int metric,
                      float* hi, float* lo, float* norms, void* stream);
 
-/* Split queries the same way: q_hi, q_lo are [nq_pad, kpad], nq_pad = round_up(nq, 256). */
+/* Split queries the same way, pre-scaled by -2 (exact): q_hi + q_lo == -2q; [nq_pad, kpad],
+ * nq_pad = round_up(nq, 256).  The contraction then yields -2 q.x and the epilogue only adds
+ * |x|^2 to obtain the ranking key. */
 int64_t vdb_flat_nqpad(int64_t nq);
 int vdb_flat_prepare_queries(const float* q, int64_t nq, int d, int64_t ld,
                              float* q_hi, float* q_lo, void* stream);
@@ -101,6 +103,11 @@ int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* nor
 int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, int64_t n, int d,
                         const float* q_hi, const float* q_lo, int64_t nq, int impl,
                         float* keys, void* stream);
+
+/* Bring-up knob for kernel timing experiments (results are WRONG for mode != 0): 2 = filter
+ * but never append a candidate, 3 = do not read the accumulators at all (contraction pipeline
+ * only).  Returns the previous mode. */
+int vdb_set_debug_mode(int mode);
 
 /* ---- multi-GPU merge ----------------------------------------------------------------- */
 /* d_all/i_all: [parts, nq, k] as written by an allgather of per-shard results (each sorted

@@ -23,6 +23,9 @@ q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32)
 shard = engine.FlatShard(base, metric, "cuda")
 del base
 code = _lib.IMPL_NAMES[impl]
+dbg = int(os.environ.get("VDB_DBG", "0"))
+if dbg:
+    _lib.load().vdb_set_debug_mode(dbg)
 for _ in range(2):
     D, I = shard.search(q.clone(), k, 0, 3.4e38, code)
 torch.cuda.synchronize()
@@ -37,5 +40,5 @@ for _ in range(reps):
     ts.append(e0.elapsed_time(e1))
 ms = float(np.median(ts))
 flops = 2.0 * nq * n * d
-print(f"[{impl}] n={n} d={d} nq={nq} k={k} {metric}: median {ms:.3f} ms (min {min(ts):.3f})  "
+print(f"[{impl} dbg={dbg}] n={n} d={d} nq={nq} k={k} {metric}: median {ms:.3f} ms (min {min(ts):.3f})  "
       f"QPS {nq / ms * 1e3:,.0f}  fp32-equiv {flops / ms / 1e9:.1f} TFLOP/s  tf32-pipe(3x) {3 * flops / ms / 1e9:.1f} TFLOP/s", flush=True)

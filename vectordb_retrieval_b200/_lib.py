@@ -36,6 +36,7 @@ SIGNATURES = {
     "vdb_flat_topk": (_i32, [_i32, _p, _p, _p, _i64, _i32, _i64, _p, _p, _i64, _i32, _i32, _f32, _i32,
                              _p, _p, _p, _sz, _p]),
     "vdb_flat_dense_keys": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _i64, _i32, _p, _p]),
+    "vdb_set_debug_mode": (_i32, [_i32]),
     "vdb_merge_topk": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_rerank_topk": (_i32, [_i32, _p, _i64, _i32, _i64, _p, _i64, _i32, _p, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_ivf_d4": (_i32, [_i32]),

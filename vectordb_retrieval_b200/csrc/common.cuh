@@ -102,36 +102,90 @@ __device__ __forceinline__ void warp_sort(uint64_t (&v)[E], int lane) {
 // ---------------------------------------------------------------------------------------------
 // Per-query candidate pool in global memory (L2 resident): CAP = 2*KP slots.  The owner
 // thread appends every key that beats its running bound `thr`; when fewer than 32 free slots
-// remain the whole warp sorts that pool, keeps the best KP and tightens `thr` to the KP-th
-// key - a valid bound because at least KP scanned rows are <= it.  Called with all 32 lanes.
+// remain the whole warp selects that pool's best KP (radix select, no sort) and tightens `thr`
+// to the KP-th key - a valid bound because at least KP scanned rows are <= it.  All 32 lanes call.
 struct PoolState {
   float thr;
   int cnt;
 };
 
-// slow path, one copy per kernel: compacts the pool of every lane flagged in `need`
+// Warp-wide selection: the value of rank `kth` (1-indexed, ascending) among the 32*E words
+// held as w[e] by the lanes, counting only words whose `live` flag is set.  MSB-first binary
+// search on the value bits with one warp-sum per bit; the bits all live words share are skipped.
+template <int E>
+__device__ __forceinline__ uint32_t warp_select_kth(const uint32_t (&w)[E], const bool (&live)[E], int kth) {
+  uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (live[e]) { mn = min(mn, w[e]); mx = max(mx, w[e]); }
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  const uint32_t diff = mn ^ mx;
+  if (diff == 0u) return mn;
+  const int top = 31 - __clz(diff);                         // highest bit where live words differ
+  uint32_t prefix = top == 31 ? 0u : (mn >> (top + 1)) << (top + 1);
+  for (int bit = top; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (live[e] && w[e] < cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c < kth) prefix = cand;                             // fewer than kth words below cand: the answer is >= cand
+  }
+  return prefix;
+}
+
+// slow path, one copy per kernel: compacts the pool of every lane flagged in `need`.
+// Keeps exactly the KP smallest (key, row) words (selection, not a sort: the pool is unordered)
+// and returns the KP-th key as the new bound.
 template <int KP>
 __device__ __noinline__ PoolState pool_compact(unsigned need, float thr, int cnt, uint64_t* pool, int lane,
                                                uint32_t* thr_shared) {
   constexpr int CAP = 2 * KP;
   constexpr int E = CAP / 32;
+  const unsigned lt_mask = (1u << lane) - 1u;
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
     uint64_t* p = reinterpret_cast<uint64_t*>(
         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(pool), src));
-    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    const int c = __shfl_sync(0xffffffffu, cnt, src);       // CAP - 32 < c <= CAP, so c >= KP
     __syncwarp();
-    uint64_t v[E];
+    uint32_t hi[E], lo[E];
+    bool live[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = e * 32 + lane;
-      v[e] = i < c ? __ldcg(p + i) : kEmpty;
+      live[e] = i < c;
+      const uint64_t w = live[e] ? __ldcg(p + i) : kEmpty;
+      hi[e] = static_cast<uint32_t>(w >> 32);
+      lo[e] = static_cast<uint32_t>(w);
     }
-    warp_sort<E>(v, lane);
+    const uint32_t kth = warp_select_kth<E>(hi, live, KP);   // ordered image of the KP-th smallest key
+    int below = 0, equal = 0;
 #pragma unroll
-    for (int e = 0; e < KP / 32; ++e) __stcg(p + e * 32 + lane, v[e]);
-    const uint32_t kth = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v[KP / 32 - 1] >> 32), 31);
+    for (int e = 0; e < E; ++e) {
+      below += (live[e] && hi[e] < kth) ? 1 : 0;
+      equal += (live[e] && hi[e] == kth) ? 1 : 0;
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    equal = __reduce_add_sync(0xffffffffu, equal);
+    uint32_t row_cut = 0xffffffffu;                         // keys equal to the bound: keep the lowest rows
+    if (below + equal > KP) {
+      bool tie[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) tie[e] = live[e] && hi[e] == kth;
+      row_cut = warp_select_kth<E>(lo, tie, KP - below);
+    }
+    int off = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool keep = live[e] && (hi[e] < kth || (hi[e] == kth && lo[e] <= row_cut));
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) __stcg(p + off + __popc(m & lt_mask), (static_cast<uint64_t>(hi[e]) << 32) | lo[e]);
+      off += __popc(m);
+    }
     if (lane == src) {
       cnt = KP;
       thr = fminf(thr, ord2f(kth));

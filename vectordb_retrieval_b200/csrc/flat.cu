@@ -62,6 +62,7 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+static int g_debug_mode = 0;
 
 // --------------------------------------------------------------------------------------------
 __global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt) {
@@ -133,7 +134,7 @@ flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ 
         pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
         for (int i = 0; i < 32; ++i) {
           const uint32_t row = static_cast<uint32_t>(b_row0) + c * 32 + i;
-          const float key = fmaf(-2.f, Ss[tid][c * 32 + i], __ldg(P.norms + row));
+          const float key = Ss[tid][c * 32 + i] + __ldg(P.norms + row);   // queries carry the -2
           if (P.dense != nullptr && live) P.dense[q * P.dense_ld + row] = key;
           if (key < thr) { pool[cnt] = pack_key(key, row); ++cnt; }
         }
@@ -206,7 +207,7 @@ flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __
       double acc = 0.0;
       for (int j = lane; j < kpad; j += 32) {
         const float xb = xh[j] + xl[j];
-        const float xq = qh[j] + ql[j];
+        const float xq = -0.5f * (qh[j] + ql[j]);   // operands hold -2q (exact scaling)
         if (metric == VDB_METRIC_L2) {
           const float df = xb - xq;
           acc += static_cast<double>(df) * static_cast<double>(df);
@@ -402,7 +403,7 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   P.thr = reinterpret_cast<uint32_t*>(w);
   P.pool_cnt = reinterpret_cast<int*>(w + off_cnt);
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
-  P.dense = dense; P.dense_ld = n_pad;
+  P.dense = dense; P.dense_ld = n_pad; P.dbg = g_debug_mode;
   const int64_t n_cnt = nq_pad * plan.n_chunks;
   flat_init_kernel<<<static_cast<unsigned>((n_cnt + 255) / 256), 256, 0, stream>>>(P.thr, nq_pad, P.pool_cnt, n_cnt);
   VDB_CHECK_CUDA(cudaGetLastError());
@@ -422,6 +423,12 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
 using namespace vdb;
 
 extern "C" {
+
+int vdb_set_debug_mode(int mode) {
+  const int old = g_debug_mode;
+  g_debug_mode = mode;
+  return old;
+}
 
 size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   int sm = 148;

@@ -10,8 +10,10 @@
 //   warp 0      TMA producer  : base tiles (hi, lo) -> 128B-swizzled smem ring
 //   warp 1      MMA issuer    : per 32-wide k-block  hi*hi + hi*lo + lo*hi  (kind::tf32, fp32 acc in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue      : tcgen05.ld 32 columns, key = |x|^2 - 2 q.x, compare against the
-//                               query's bound, append the rare survivors to the query's pool
+//   warps 4..7  epilogue      : tcgen05.ld 32 columns, key = acc + |x|^2 (queries are pre-scaled by
+//                               -2, the tile's norms are bulk-copied to smem by the producer),
+//                               compare against the query's bound, append the rare survivors to
+//                               the query's pool
 // kCtaGroup == 2: two CTAs of a cluster form one 256 x 256 UMMA (cta_group::2); each loads half
 // of every base tile, which halves L2->smem traffic per SM.
 #pragma once
@@ -35,6 +37,7 @@ struct FlatScanParams {
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
   float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
   int64_t dense_ld;
+  int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld
 };
 
 namespace tc {
@@ -43,7 +46,7 @@ constexpr int kStages = 3;
 constexpr int kBlockRows = 128;                      // rows per operand block (A or B half)
 constexpr int kBlockBytes = kBlockRows * 128;        // 16 KB: 128 rows x 32 fp32, SWIZZLE_128B
 constexpr int kMaxResidentKb = 4;                    // query tile stays in smem when kpad <= 128
-constexpr int kNormStageBytes = 4 * 2 * 32 * 4;      // per epilogue warp, double buffered
+constexpr int kNormRingBytes = 2 * 256 * 4;        // |x|^2 of two tiles (<= 256 rows each)
 constexpr int kBarrierBytes = 256;
 
 template <bool kAResident>
@@ -51,7 +54,7 @@ constexpr int smem_bytes() {
   // resident: A_hi/A_lo [4] + ring of {B_hi, B_lo};  streamed: ring of {A_hi, A_lo, B_hi, B_lo}
   return (kAResident ? 2 * kMaxResidentKb * kBlockBytes + kStages * 2 * kBlockBytes
                      : kStages * 4 * kBlockBytes) +
-         kNormStageBytes + kBarrierBytes + 1024 /* manual 1024-byte alignment slack */;
+         kNormRingBytes + kBarrierBytes;   // dynamic smem must start 1024-byte aligned (checked)
 }
 }  // namespace tc
 
@@ -69,21 +72,26 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // align inside the shared window (pointer arithmetic on the array keeps LDS/STS addressing)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) {   // SWIZZLE_128B operand blocks need 1024-byte alignment
+    if (threadIdx.x == 0) printf("vdb: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   // operand blocks
   uint8_t* a_res = smem;                                                        // [2][kMaxResidentKb][16K] (hi, lo)
   uint8_t* ring = smem + (kAResident ? 2 * tc::kMaxResidentKb * tc::kBlockBytes : 0);
   constexpr int kStageBytes = (kAResident ? 2 : 4) * tc::kBlockBytes;
-  float* norm_stage = reinterpret_cast<float*>(ring + tc::kStages * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(norm_stage) + tc::kNormStageBytes);
+  float* norm_ring = reinterpret_cast<float*>(ring + tc::kStages * kStageBytes);   // [2][UMMA_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(norm_ring) + tc::kNormRingBytes);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's are used)
   uint64_t* empty_bar = bars + tc::kStages;        // [kStages]  MMA -> TMA          (every CTA)
   uint64_t* a_full_bar = bars + 2 * tc::kStages;   //            resident A landed   (leader)
   uint64_t* a_empty_bar = a_full_bar + 1;          //            resident A consumed (every CTA)
   uint64_t* tmem_full_bar = a_empty_bar + 1;       // [2]        MMA -> epilogue     (every CTA)
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]        epilogue -> MMA     (leader)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* norm_full_bar = tmem_empty_bar + 2;    // [2]        norms landed        (every CTA, local)
+  uint64_t* norm_empty_bar = norm_full_bar + 2;    // [2]        norms consumed      (every CTA, local)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(norm_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,7 +109,10 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     for (int s = 0; s < tc::kStages; ++s) { mbar_init(full_bar + s, kCtaGroup); mbar_init(empty_bar + s, 1); }
     mbar_init(a_full_bar, kCtaGroup);
     mbar_init(a_empty_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar + b, 1); mbar_init(tmem_empty_bar + b, 4 * kCtaGroup); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar + b, 1); mbar_init(tmem_empty_bar + b, 4 * kCtaGroup);
+      mbar_init(norm_full_bar + b, 1); mbar_init(norm_empty_bar + b, 4);
+    }
     fence_barrier_init();
   }
   if (kCtaGroup == 2) cluster_sync_all();   // peer barriers must exist before any remote arrive
@@ -114,7 +125,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
-      int stage = 0; uint32_t phase = 0; int item_iter = 0;
+      int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
       for (int item = cluster_id; item < n_items; item += n_clusters, ++item_iter) {
         const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
         const int t0 = chunk * P.tiles_per_chunk;
@@ -129,7 +140,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           if (is_leader) mbar_arrive_expect_tx(a_full_bar, kCtaGroup * P.kb * 2 * tc::kBlockBytes);
           else mbar_arrive_cluster(a_full_bar, 0);
         }
-        for (int t = t0; t < t1; ++t) {
+        for (int t = t0; t < t1; ++t, ++tile_iter) {
           const int b_row0 = t * UMMA_N + cta_rank * 128;
           for (int kbi = 0; kbi < P.kb; ++kbi) {
             mbar_wait(empty_bar + stage, phase ^ 1);
@@ -144,6 +155,13 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             else mbar_arrive_cluster(full_bar + stage, 0);
             if (++stage == tc::kStages) { stage = 0; phase ^= 1; }
           }
+          // |x|^2 of the whole tile for this CTA's epilogue (issued after the operand loads, so the
+          // wait for the previous user of this buffer never delays them)
+          const uint32_t nbuf = tile_iter & 1;
+          mbar_wait(norm_empty_bar + nbuf, ((tile_iter >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(norm_full_bar + nbuf, UMMA_N * 4);
+          bulk_load_1d(norm_ring + nbuf * UMMA_N, P.norms + static_cast<int64_t>(t) * UMMA_N, UMMA_N * 4,
+                       norm_full_bar + nbuf);
         }
       }
     }
@@ -193,9 +211,15 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     }
   } else if (warp >= 4) {
     // ===================================== epilogue: filter keys against the running bound ==
+    // Queries arrive scaled by -2, so key_j = acc_j + |x_j|^2.  The tile's norms were put into
+    // shared memory by the producer (bulk copy, one barrier), every lane reads them as broadcast
+    // 128-bit loads.  Per 32-column chunk a branch-free min tree decides whether any key of this
+    // lane beats its bound; only then is the (rare) append code entered.  The chunk loop is a
+    // runtime loop over two register buffers so the steady state stays small in the I-cache.
     const int ew = warp - 4;                       // TMEM lane quarter == warp % 4
-    float* nst = norm_stage + ew * 64;
     constexpr int NCH = UMMA_N / 32;               // 32-column chunks per tile
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    uint32_t va[32], vb[32];
     uint32_t tile_iter = 0;
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
@@ -207,77 +231,81 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       uint32_t* thr_g = P.thr + q;
       int cnt = 0;
       float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
-      // norms of the tile, lane l holds columns l, l+32, ...; fetched one tile ahead
-      float nrm_next[NCH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) nrm_next[c] = __ldg(P.norms + static_cast<int64_t>(t0) * UMMA_N + c * 32 + lane);
       for (int t = t0; t < t1; ++t, ++tile_iter) {
-        const uint32_t buf = tile_iter & 1;
-        float nrm[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) nrm[c] = nrm_next[c];
-        // loads whose latency hides behind this tile: the shared bound and the next tile's norms
+        const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
+        // the shared bound is read here and folded in after the tile: its latency hides behind the tile
         const float thr_seen = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
-        if (t + 1 < t1) {
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) nrm_next[c] = __ldg(P.norms + static_cast<int64_t>(t + 1) * UMMA_N + c * 32 + lane);
-        }
-        mbar_wait(tmem_full_bar + buf, (tile_iter >> 1) & 1);
-        tc_fence_after();
         const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * UMMA_N;
-        uint32_t va[32], vb[32];
+        const float* nb = norm_ring + buf * UMMA_N;
+        mbar_wait(norm_full_bar + buf, ph);
+        mbar_wait(tmem_full_bar + buf, ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + buf * UMMA_N;
+        auto release_tmem = [&]() {                // every column of this accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (is_leader) mbar_arrive(tmem_empty_bar + buf);
+            else mbar_arrive_cluster(tmem_empty_bar + buf, 0);
+          }
+        };
+        if (P.dbg == 3) {   // pipeline-only timing: skip the accumulator read-out entirely
+          release_tmem();
+          if (lane == 0) mbar_arrive(norm_empty_bar + buf);
+          continue;
+        }
         tmem_ld_32x32(taddr, va);
 
-        auto consume = [&](const uint32_t (&v)[32], int c) {
-          float* ns = nst + (c & 1) * 32;
-          ns[lane] = nrm[c];
-          __syncwarp();
+        auto consume = [&](uint32_t (&v)[32], int c) {
+          const float4* n4 = reinterpret_cast<const float4*>(nb + c * 32);
           const uint32_t rbase = row0 + c * 32;
+          float gm[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 n4 = *reinterpret_cast<const float4*>(ns + g * 4);
-            const float k0 = fmaf(-2.f, __uint_as_float(v[g * 4 + 0]), n4.x);
-            const float k1 = fmaf(-2.f, __uint_as_float(v[g * 4 + 1]), n4.y);
-            const float k2 = fmaf(-2.f, __uint_as_float(v[g * 4 + 2]), n4.z);
-            const float k3 = fmaf(-2.f, __uint_as_float(v[g * 4 + 3]), n4.w);
-            if (kDense) {
-              if (live) {
-                float* dp = P.dense + q * P.dense_ld + rbase + g * 4;
-                dp[0] = k0; dp[1] = k1; dp[2] = k2; dp[3] = k3;
-              }
+            const float4 nn = n4[g];
+            const float k0 = __uint_as_float(v[g * 4 + 0]) + nn.x, k1 = __uint_as_float(v[g * 4 + 1]) + nn.y;
+            const float k2 = __uint_as_float(v[g * 4 + 2]) + nn.z, k3 = __uint_as_float(v[g * 4 + 3]) + nn.w;
+            v[g * 4 + 0] = __float_as_uint(k0); v[g * 4 + 1] = __float_as_uint(k1);
+            v[g * 4 + 2] = __float_as_uint(k2); v[g * 4 + 3] = __float_as_uint(k3);
+            gm[g] = fminf(fminf(k0, k1), fminf(k2, k3));
+          }
+          const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])),
+                                fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+          if (kDense) {
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) P.dense[q * P.dense_ld + rbase + i] = __uint_as_float(v[i]);
             }
-            if (fminf(fminf(k0, k1), fminf(k2, k3)) < thr) {     // rare: some key beats the bound
-              if (k0 < thr) { pool[cnt] = pack_key(k0, rbase + g * 4 + 0); ++cnt; }
-              if (k1 < thr) { pool[cnt] = pack_key(k1, rbase + g * 4 + 1); ++cnt; }
-              if (k2 < thr) { pool[cnt] = pack_key(k2, rbase + g * 4 + 2); ++cnt; }
-              if (k3 < thr) { pool[cnt] = pack_key(k3, rbase + g * 4 + 3); ++cnt; }
+          }
+          if (m < thr && P.dbg != 2) {           // some key of this lane beats its bound (rare)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (gm[g] < thr) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float key = __uint_as_float(v[g * 4 + u]);
+                  if (key < thr) { pool[cnt] = pack_key(key, rbase + g * 4 + u); ++cnt; }
+                }
+              }
             }
           }
         };
 
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < NCH; c += 2) {
-          // chunk c is in flight in va: wait, start chunk c+1 into vb, then filter va under its latency
+          // chunk c is in flight in va: wait, start chunk c+1 into vb, filter va under that latency
           tmem_ld_wait();
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
           pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
           consume(va, c);
           tmem_ld_wait();
-          if (c + 2 < NCH) {
-            tmem_ld_32x32(taddr + (c + 2) * 32, va);
-          } else {
-            // every column of this accumulator is in registers: hand the buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (is_leader) mbar_arrive(tmem_empty_bar + buf);
-              else mbar_arrive_cluster(tmem_empty_bar + buf, 0);
-            }
-          }
+          if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+          else release_tmem();
           pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
           consume(vb, c + 1);
         }
+        __syncwarp();                              // all lanes are done with this tile's norms
+        if (lane == 0) mbar_arrive(norm_empty_bar + buf);
         thr = fminf(thr, thr_seen);
       }
       P.pool_cnt[q * P.n_chunks + chunk] = cnt;

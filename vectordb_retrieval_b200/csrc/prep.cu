@@ -61,7 +61,7 @@ __device__ __forceinline__ float tf32_round(float x) {
 // hi/lo split into the padded operand layout [n_pad, kpad]; also |x|^2 (L2) / 0 (IP) / +inf (pad rows).
 // One warp per output row; rows >= n and columns >= d are written as zero.
 __global__ void split_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, int64_t ld,
-                                  int kpad, int metric, float* __restrict__ hi, float* __restrict__ lo,
+                                  int kpad, int metric, float scale, float* __restrict__ hi, float* __restrict__ lo,
                                   float* __restrict__ norms) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -72,7 +72,7 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int64_t n, int64_
   const bool live = row < n;
   const float* r = x + (live ? row : 0) * ld;
   for (int j = lane; j < kpad; j += 32) {
-    const float v = (live && j < d) ? r[j] : 0.f;
+    const float v = (live && j < d) ? r[j] * scale : 0.f;   // scale is a power of two: exact
     const float vh = tf32_round(v);
     h[j] = vh;
     l[j] = v - vh;
@@ -130,7 +130,7 @@ int vdb_flat_prepare(const float* x, int64_t n, int d, int64_t ld, int metric, f
   const int64_t n_pad = vdb_flat_npad(n);
   const int64_t blocks = (n_pad * 32 + 255) / 256;
   split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, n, n_pad, d, ld, vdb_flat_kpad(d), metric, hi, lo, norms);
+      x, n, n_pad, d, ld, vdb_flat_kpad(d), metric, 1.f, hi, lo, norms);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -140,7 +140,7 @@ int vdb_flat_prepare_queries(const float* q, int64_t nq, int d, int64_t ld, floa
   const int64_t nq_pad = vdb_flat_nqpad(nq);
   const int64_t blocks = (nq_pad * 32 + 255) / 256;
   split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      q, nq, nq_pad, d, ld, vdb_flat_kpad(d), VDB_METRIC_IP, q_hi, q_lo, nullptr);
+      q, nq, nq_pad, d, ld, vdb_flat_kpad(d), VDB_METRIC_IP, -2.f, q_hi, q_lo, nullptr);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

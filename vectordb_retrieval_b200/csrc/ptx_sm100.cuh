@@ -86,6 +86,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uin
   }
 }
 
+// 1-D bulk copy global -> this CTA's shared memory (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -149,7 +157,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // Shared-memory matrix descriptor, K-major operand tile whose rows are exactly one 128-byte
 // swizzle atom wide (32 fp32): 8-row groups are 1024 bytes apart (SBO), LBO unused,
 // descriptor version 1 (sm_100), layout SWIZZLE_128B.

@@ -50,6 +50,40 @@ def to_device_f32(x, dev: torch.device, chunk_rows: int = 1 << 20) -> torch.Tens
     return out
 
 
+def queries_to_device(queries, dev: torch.device, dimension: Optional[int] = None) -> torch.Tensor:
+    """Host query batch (numpy, any dtype/layout; 1-D = one query) -> fresh [nq, d] fp32 device tensor.
+    The copy is asynchronous when the host array is pinned; the kernels that follow are ordered
+    behind it on the current stream.  Raises RuntimeError on a shape mismatch (never ValueError:
+    the reference harness swallows that and degrades to per-query search)."""
+    if isinstance(queries, torch.Tensor):
+        q = queries.to(device=dev, dtype=torch.float32)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        return q.contiguous().clone() if q.data_ptr() == queries.data_ptr() else q.contiguous()
+    q = np.asarray(queries)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    if q.ndim != 2 or (dimension is not None and q.shape[1] != dimension):
+        raise RuntimeError(f"query batch has shape {q.shape}, expected [nq, {dimension}]")
+    if q.dtype != np.float32 or not q.flags["C_CONTIGUOUS"]:
+        q = np.ascontiguousarray(q, dtype=np.float32)
+    if not q.flags["WRITEABLE"]:
+        q = q.copy()
+    out = torch.empty(q.shape, dtype=torch.float32, device=dev)
+    out.copy_(torch.from_numpy(q), non_blocking=True)
+    return out
+
+
+def results_to_host(dist: torch.Tensor, idx: torch.Tensor) -> Tuple[np.ndarray, np.ndarray]:
+    """Device results -> fresh numpy arrays owned by the caller.  Lands in pinned memory from
+    torch's caching host allocator (no extra host memcpy); the arrays keep their blocks alive."""
+    hd = torch.empty(dist.shape, dtype=dist.dtype, pin_memory=True)
+    hi = torch.empty(idx.shape, dtype=idx.dtype, pin_memory=True)
+    hd.copy_(dist, non_blocking=True)
+    hi.copy_(idx, non_blocking=True)
+    torch.cuda.current_stream(dist.device).synchronize()
+    return hd.numpy(), hi.numpy()
+
+
 def normalize_rows_(x: torch.Tensor) -> torch.Tensor:
     """In-place row normalisation on device (zero rows stay zero)."""
     lib = _lib.load()
