@@ -15,6 +15,8 @@
  *                                                  src/algorithms/approximate_search.py:39-51,87
  *   vdb_rerank_topk  FaissSearcher._batch_search_lsh_rerank  src/algorithms/modular.py:483-532
  *                    LSHSearcher._compute_distances + argsort src/algorithms/lsh.py:242-283
+ *   vdb_lsh_encode / vdb_hamming_topk
+ *                    faiss.IndexLSH add/search     src/algorithms/modular.py:215-216,477
  *   vdb_merge_topk   (new) merge of per-GPU top-k lists after the NCCL allgather
  *
  * Conventions
@@ -52,6 +54,8 @@ enum { VDB_IMPL_AUTO = 0, VDB_IMPL_TCGEN05 = 1, VDB_IMPL_TCGEN05_1CTA = 2, VDB_I
 
 const char* vdb_last_error(void);
 int vdb_abi_version(void);
+/* kernels launched by this library since it was loaded (bench.py reports the delta) */
+int64_t vdb_launch_count(void);
 /* number of SMs of the current device (grid sizing / reporting) */
 int vdb_sm_count(int* out);
 
@@ -106,8 +110,16 @@ int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, in
 
 /* Bring-up knob for kernel timing experiments (results are WRONG for mode != 0): 2 = filter
  * but never append a candidate, 3 = do not read the accumulators at all (contraction pipeline
- * only).  Returns the previous mode. */
+ * only), 5 = start from the bounds the previous call left in the workspace (perfect warm start),
+ * 6 = empty a full pool instead of compacting it.  Returns the previous mode. */
 int vdb_set_debug_mode(int mode);
+
+/* Measurement hook for bench.py's roofline leg: while enabled, every vdb_flat_topk call brackets
+ * its scan kernel with a pair of CUDA events on the launching stream (up to 512 calls).
+ * vdb_flat_timing_read waits for the recorded events, writes the scan durations in milliseconds
+ * in call order, stores their number in *n_out and clears the log. */
+int vdb_flat_timing_enable(int on);
+int vdb_flat_timing_read(float* ms, int max_records, int* n_out);
 
 /* ---- multi-GPU merge ----------------------------------------------------------------- */
 /* d_all/i_all: [parts, nq, k] as written by an allgather of per-shard results (each sorted
@@ -125,6 +137,21 @@ int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld,
                     const int64_t* cand, int64_t nq, int c, const float* q, int64_t ld_q,
                     int k, int flags, float pad_value, float* out_d, int64_t* out_i, void* stream);
 
+/* ---- LSH sign codes + Hamming top-k (candidate generator in front of the rerank) ------- */
+/* Code layout: [n, words] uint32, words = vdb_lsh_code_words(nbits) = 4 * ceil(nbits / 128)
+ * (16-byte aligned rows, unused high bits zero); bit b of a row = [ x . P[b] >= 0 ].
+ * proj_t: the projection transposed and padded, [d, words * 32] fp32 (column b = P[b]). */
+int vdb_lsh_code_words(int nbits);
+int vdb_lsh_encode(const float* x, int64_t n, int d, int64_t ld, const float* proj_t, int nbits,
+                   uint32_t* codes, void* stream);
+/* k smallest Hamming distances per query, ordered by (distance, id): out_d [nq,k] float32
+ * (the integer distance), out_i [nq,k] int64 = row + id_offset.  out_* must be pre-filled with
+ * the padding the caller wants for k > n.  nbits <= 1024.  Replaces faiss.IndexLSH.search. */
+size_t vdb_hamming_topk_workspace_bytes(int64_t nq, int nbits);
+int vdb_hamming_topk(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits,
+                     int k, int64_t id_offset, float* out_d, int64_t* out_i,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- IVF-Flat -------------------------------------------------------------------------- */
 /* Inverted lists, device layout ("interleaved-32"): list l occupies blocks
  * [blk_off[l], blk_off[l+1]) ; block b holds 32 vectors as float4 [d4][32 lanes]
@@ -134,6 +161,11 @@ int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld,
 int vdb_ivf_d4(int d);
 /* counts[l] += number of rows assigned to list l (assign in [0,nlist); counts pre-zeroed) */
 int vdb_ivf_count(const int32_t* assign, int64_t n, int nlist, int32_t* counts, void* stream);
+/* k-means centroid update (IVF training): sums[l,:] += x[i,:] and counts[l] += 1 with
+ * l = assign[i] (int64, as written by vdb_flat_topk with k = 1; out-of-range = skipped).
+ * sums [nlist,d] fp32 and counts [nlist] int32 are pre-zeroed by the caller. */
+int vdb_kmeans_accumulate(const float* x, int64_t n, int d, int64_t ld, const int64_t* assign,
+                          int nlist, float* sums, int32_t* counts, void* stream);
 /* scatter rows into the interleaved layout; blk_off [nlist+1] int32 (prefix sum of
  * ceil(count/32)), cursor [nlist] int32 zeroed scratch.  Slot order inside a list is
  * arbitrary; search results never depend on it (the scan orders by (distance, id)). */

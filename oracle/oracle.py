@@ -259,6 +259,42 @@ def rerank_search(base: np.ndarray, candidates: np.ndarray, queries: np.ndarray,
     return out_d, out_i
 
 
+# --------------------------------------------------------------------------- FAISS IndexLSH (sign codes)
+def lsh_sign_codes(x: np.ndarray, projection: np.ndarray) -> np.ndarray:
+    """Sign bits of a random projection, packed little-endian into uint32 words padded to a
+    multiple of 128 bits: bit b = [ x . P[b] >= 0 ].  Restates ``faiss.IndexLSH.add`` /
+    ``sa_encode`` as reached from src/algorithms/modular.py:215-216 [FAISS-upstream: IndexLSH
+    with the default ``rotate_data`` applies a random d x nbits matrix and thresholds at 0;
+    FAISS's own RNG is not reproduced - parity unpinned, the projection is an input here].
+    Returns (codes [n, words] uint32, dots [n, nbits] float64) - the dots let a test skip bits
+    that sit on the decision boundary."""
+    dots = x.astype(np.float64) @ projection.astype(np.float64).T
+    bits = dots >= 0
+    nbits = projection.shape[0]
+    words = (nbits + 127) // 128 * 4
+    padded = np.zeros((x.shape[0], words * 32), dtype=bool)
+    padded[:, :nbits] = bits
+    codes = np.packbits(padded.reshape(x.shape[0], words, 32), axis=2, bitorder="little").view(np.uint32).reshape(x.shape[0], words)
+    return codes, dots
+
+
+def hamming_topk(codes: np.ndarray, qcodes: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """``faiss.IndexLSH.search`` as called at src/algorithms/modular.py:477: the k smallest
+    Hamming distances per query [FAISS-upstream; tie order unspecified there].  Deterministic
+    (distance, id) order; k > n pads with (+inf, -1)."""
+    n, nq = codes.shape[0], qcodes.shape[0]
+    out_d = np.full((nq, k), np.inf, dtype=np.float32)
+    out_i = np.full((nq, k), -1, dtype=np.int64)
+    cb = np.unpackbits(codes.view(np.uint8), axis=1)
+    for r in range(nq):
+        qb = np.unpackbits(qcodes[r:r + 1].view(np.uint8), axis=1)
+        dist = (cb != qb).sum(axis=1)
+        order = np.lexsort((np.arange(n), dist))[:k]
+        out_d[r, :order.size] = dist[order]
+        out_i[r, :order.size] = order
+    return out_d, out_i
+
+
 # --------------------------------------------------------------------------- Python LSH (lsh.py)
 class LSHTables:
     """Restatement of ``LSHIndexer.build`` (src/algorithms/lsh.py:95-138).

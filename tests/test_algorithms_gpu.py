@@ -1,0 +1,290 @@
+"""GPU tests of the reference-facing classes: the reference's own boundary tests
+(tests/test_composite_algorithm.py, tests/test_benchmark_runner_modular.py) restated against the
+CUDA-backed classes, plus parity with the oracle / golden fixtures through the public API."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle  # checker only
+from oracle.gen_golden import linear_inputs, random20k_inputs, rerank_inputs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def A():
+    import vectordb_retrieval_b200.algorithms as algorithms
+    from vectordb_retrieval_b200 import _lib
+    _lib.load()
+    return algorithms
+
+
+def _check(ref, got, rtol=1e-5, atol=0.0):
+    res = oracle.compare_topk(ref[0], ref[1], got[0], got[1], rtol=rtol, atol=atol)
+    assert res["ok"], res
+
+
+def test_composite_bruteforce_linear_matches_numpy(A):
+    """reference tests/test_composite_algorithm.py:29-58 (4-point L2 known answer)."""
+    vectors = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]], dtype=np.float32)
+    queries = np.array([[0.1, 0.1], [0.9, 0.8]], dtype=np.float32)
+    algo = A.CompositeAlgorithm(name="exact_composite", dimension=2, metric="l2",
+                                indexer={"type": "BruteForceIndexer"}, searcher={"type": "LinearSearcher"})
+    algo.build_index(vectors)
+    dist, idx = algo.batch_search(queries, k=2)
+    expected = np.argsort(np.linalg.norm(vectors[None, :, :] - queries[:, None, :], axis=2), axis=1)[:, :2]
+    np.testing.assert_array_equal(idx, expected)
+    assert dist.shape == (2, 2) and dist.dtype == np.float32 and idx.dtype == np.int64
+    d1, i1 = algo.search(queries[0], k=2)
+    np.testing.assert_array_equal(i1, expected[0])
+    np.testing.assert_allclose(d1, dist[0])
+
+
+def test_composite_requires_indexer_and_searcher(A):
+    """reference tests/test_composite_algorithm.py:88-105."""
+    with pytest.raises(ValueError):
+        A.CompositeAlgorithm(name="x", dimension=4, indexer={}, searcher={"type": "LinearSearcher"})
+    with pytest.raises(ValueError):
+        A.CompositeAlgorithm(name="x", dimension=4, indexer={"type": "BruteForceIndexer"}, searcher={})
+    with pytest.raises(ValueError):
+        A.CompositeAlgorithm(name="x", dimension=4, indexer={"name": "no_type"}, searcher={"type": "LinearSearcher"})
+    with pytest.raises(ValueError):
+        A.get_algorithm_instance("NoSuchAlgorithm", 4)
+    algo = A.get_algorithm_instance("ExactSearch", 4, name="e")
+    with pytest.raises(RuntimeError):
+        algo.batch_search(np.zeros((1, 4), dtype=np.float32), 1)
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_linear_searcher_matches_reference_golden(A, metric):
+    g = np.load(os.path.join(GOLDEN, "linear_searcher.npz"))
+    base, queries = linear_inputs()
+    algo = A.get_algorithm_instance("Composite", base.shape[1], name="lin", metric=metric,
+                                    indexer={"type": "BruteForceIndexer"}, searcher={"type": "LinearSearcher"})
+    atol = 0.0 if metric == "l2" else 2e-6 * (1 if metric == "cosine" else 40)
+    algo.build_index(base)
+    dist, idx = algo.batch_search(queries, 10)
+    _check((g[f"{metric}_D"], g[f"{metric}_I"]), (dist, idx), atol=atol)
+    d1, i1 = algo.search(queries[0], 10)
+    np.testing.assert_array_equal(i1, idx[0])
+    algo.build_index(base[:6])                                     # k > n: (+inf, -1) padding
+    dist, idx = algo.batch_search(queries[:3], 8)
+    np.testing.assert_array_equal(idx, g[f"{metric}_pad_I"])
+    _check((g[f"{metric}_pad_D"], g[f"{metric}_pad_I"]), (dist, idx), atol=atol)
+    assert np.isinf(dist[:, 6:]).all() and (idx[:, 6:] == -1).all()
+
+
+def test_exact_search_faiss_conventions(A):
+    base, queries = linear_inputs()
+    # float64, non-contiguous input must be accepted (memmap / slicing in the harness)
+    wide = np.zeros((base.shape[0], base.shape[1] * 2), dtype=np.float64)
+    wide[:, ::2] = base
+    for metric, ometric in (("l2", "l2"), ("ip", "ip"), ("cosine", "ip")):       # 'cosine' silently means raw IP (exact_search.py:23)
+        algo = A.get_algorithm_instance("ExactSearch", base.shape[1], name="exact", metric=metric)
+        algo.build_index(wide[:, ::2])
+        dist, idx = algo.batch_search(queries.astype(np.float64), 20)
+        ref = oracle.faiss_flat_search(base, queries, 20, ometric)
+        _check(ref, (dist, idx), atol=0.0 if ometric == "l2" else 1e-4)
+        assert algo.get_memory_usage() > 0 and algo.get_operations()["ndis"] == queries.shape[0] * base.shape[0]
+    # k > n pads with (-1, FLT_MAX)
+    algo = A.get_algorithm_instance("ExactSearch", base.shape[1], name="exact", metric="l2")
+    algo.build_index(base[:7])
+    dist, idx = algo.batch_search(queries[:3], 10)
+    assert (idx[:, 7:] == -1).all() and (dist[:, 7:] == np.finfo(np.float32).max).all()
+    json.dumps(algo.get_parameters())
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_faiss_searcher_lsh_rerank_with_injected_candidates(A, metric):
+    """reference tests/test_composite_algorithm.py:169-226: a fake index object supplies candidates
+    (here the golden generator's candidate matrix), the searcher re-scores them exactly."""
+    g = np.load(os.path.join(GOLDEN, "faiss_lsh_rerank.npz"))
+    base, queries, cand = rerank_inputs()
+
+    class FakeLSHIndex:
+        ntotal = base.shape[0]
+
+        def search(self, q, k):
+            assert k == cand.shape[1]
+            return np.zeros((q.shape[0], k), dtype=np.float32), cand[: q.shape[0]]
+
+    searcher = A.FaissSearcher("s", base.shape[1], metric, lsh_rerank=True, lsh_candidate_multiplier=6.0)   # candidate_k = 60
+    meta = {"metric": metric, "faiss_index_kind": "lsh"}
+    if metric == "cosine":
+        meta["normalize_queries"] = True
+    searcher.attach(A.IndexArtifact(kind="faiss", data=FakeLSHIndex(), metadata=meta), base)
+    dist, idx = searcher.batch_search(queries, 10)
+    np.testing.assert_array_equal(idx, g[f"{metric}_I"])
+    np.testing.assert_allclose(dist, g[f"{metric}_D"], rtol=1e-5, atol=2e-6)
+
+
+def test_reversed_candidates_kat(A):
+    """reference tests/test_composite_algorithm.py:169-226: candidates arrive worst-first."""
+    rng = np.random.RandomState(3)
+    base = rng.randn(50, 8).astype(np.float32)
+
+    class Reversed:
+        ntotal = 50
+
+        def search(self, q, k):
+            return np.zeros((q.shape[0], k), dtype=np.float32), np.tile(np.arange(k - 1, -1, -1), (q.shape[0], 1))
+
+    s = A.FaissSearcher("s", 8, "l2", lsh_candidate_multiplier=4.0)
+    s.attach(A.IndexArtifact(kind="faiss", data=Reversed(), metadata={"metric": "l2", "faiss_index_kind": "lsh"}), base)
+    dist, idx = s.batch_search(base[:1], 3)
+    assert idx[0, 0] == 0 and abs(dist[0, 0]) < 1e-6
+
+
+def test_python_lsh_matches_reference_golden_and_published_recall(A):
+    """Golden outputs of the unmodified reference LSHIndexer+LSHSearcher, and the published
+    recall@10 = 0.31914062499999996 (benchmark_20260305_070532/random/lsh_results.json:46)."""
+    g = np.load(os.path.join(GOLDEN, "python_lsh.npz"))
+    base, queries, _ = random20k_inputs()
+    algo = A.get_algorithm_instance("Composite", 64, name="lsh", metric="l2",
+                                    indexer={"type": "LSHIndexer", "num_tables": 12, "hash_size": 4, "bucket_width": 20.0, "seed": 42},
+                                    searcher={"type": "LSHSearcher", "candidate_multiplier": 64, "fallback_to_bruteforce": False})
+    algo.build_index(base)
+    dist, idx = algo.batch_search(queries, 20)
+    _check((g["r20k_D"], g["r20k_I"]), (dist, idx), atol=1e-6)
+    gt = g["r20k_gt20"]
+    assert oracle.recall_at_k(gt, idx, 10) == pytest.approx(0.31914062499999996, abs=1e-12) == float(g["r20k_recall10"])
+    assert oracle.recall_at_k(gt, idx, 1) == pytest.approx(0.34765625, abs=1e-12) == float(g["r20k_recall1"])
+    # the exact path on the same data reproduces the reference's exact rows (recall 1.0 published)
+    exact = A.get_algorithm_instance("Composite", 64, name="exact", metric="l2", indexer={"type": "BruteForceIndexer"},
+                                     searcher={"type": "LinearSearcher"})
+    exact.build_index(base)
+    d, i = exact.batch_search(queries[:64], 20)
+    _check((g["r20k_exact_D"], g["r20k_exact_I"]), (d, i))
+    assert oracle.recall_at_k(gt[:64], i, 10) == 1.0
+
+
+def test_python_lsh_reference_kat_outputs(A):
+    """Outputs of the unmodified reference on its own two LSH KAT set-ups (tests/golden/python_lsh.npz)."""
+    g = np.load(os.path.join(GOLDEN, "python_lsh.npz"))
+    rng = np.random.RandomState(7)
+    train = rng.randn(128, 16).astype(np.float32)
+    train /= np.linalg.norm(train, axis=1, keepdims=True)
+    algo = A.get_algorithm_instance("Composite", 16, name="lsh_cos", metric="cosine",
+                                    indexer={"type": "LSHIndexer", "num_tables": 12, "hash_size": 16, "seed": 7},
+                                    searcher={"type": "LSHSearcher", "candidate_multiplier": 12.0, "fallback_to_bruteforce": True})
+    algo.build_index(train)
+    d, i = algo.batch_search(train[:5].copy(), 4)
+    _check((g["kat_cos_D"], g["kat_cos_I"]), (d, i), atol=2e-6)
+    rng = np.random.RandomState(11)
+    train = rng.randn(160, 8).astype(np.float32)
+    algo = A.get_algorithm_instance("Composite", 8, name="lsh_l2", metric="l2",
+                                    indexer={"type": "LSHIndexer", "num_tables": 10, "hash_size": 12, "bucket_width": 3.0, "seed": 11},
+                                    searcher={"type": "LSHSearcher", "candidate_multiplier": 10.0, "fallback_to_bruteforce": True})
+    algo.build_index(train)
+    d, i = algo.batch_search(train[10:20].copy(), 4)
+    _check((g["kat_l2_D"], g["kat_l2_I"]), (d, i), atol=2e-6)
+
+
+def test_lsh_self_retrieval_kats(A):
+    """reference tests/test_composite_algorithm.py:108-166: identical vectors come back first with distance ~0."""
+    rng = np.random.RandomState(7)
+    vectors = rng.randn(128, 16).astype(np.float32)
+    vectors /= np.linalg.norm(vectors, axis=1, keepdims=True)
+    algo = A.get_algorithm_instance("LSH", 16, name="lsh_cos", metric="cosine", num_tables=12, hash_size=16,
+                                    candidate_multiplier=12.0, seed=42)
+    algo.build_index(vectors)
+    dist, idx = algo.batch_search(vectors[:5], 1)
+    np.testing.assert_array_equal(idx[:, 0], np.arange(5))
+    np.testing.assert_allclose(dist[:, 0], 0.0, atol=1e-6)
+    rng = np.random.RandomState(11)
+    vectors = rng.randn(160, 8).astype(np.float32)
+    comp = A.get_algorithm_instance("Composite", 8, name="lsh_l2", metric="l2",
+                                    indexer={"type": "LSHIndexer", "num_tables": 10, "hash_size": 6, "bucket_width": 3.0, "seed": 1},
+                                    searcher={"type": "LSHSearcher", "candidate_multiplier": 16.0})
+    comp.build_index(vectors)
+    dist, idx = comp.batch_search(vectors[10:20], 1)
+    np.testing.assert_array_equal(idx[:, 0], np.arange(10, 20))
+    np.testing.assert_allclose(dist[:, 0], 0.0, atol=1e-6)
+    # no bucket hit and no fallback -> padding; with fallback -> exact scan
+    far = np.full((1, 8), 1e4, dtype=np.float32)
+    nofb = A.get_algorithm_instance("LSH", 8, name="x", metric="l2", num_tables=2, hash_size=8, bucket_width=0.5,
+                                    fallback_to_bruteforce=False)
+    nofb.build_index(vectors)
+    d, i = nofb.batch_search(far, 3)
+    assert (i == -1).all() and np.isinf(d).all()
+    fb = A.get_algorithm_instance("LSH", 8, name="x", metric="l2", num_tables=2, hash_size=8, bucket_width=0.5)
+    fb.build_index(vectors)
+    d, i = fb.batch_search(far, 3)
+    _check(oracle.linear_search(vectors, far, 3, "l2"), (d, i))
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_ivf_pipeline_given_same_centroids_and_recall(A, metric):
+    rng = np.random.RandomState(5)
+    centers = rng.randn(32, 24).astype(np.float32) * 2
+    base = (centers[rng.randint(0, 32, 20000)] + 0.4 * rng.randn(20000, 24)).astype(np.float32)
+    queries = (centers[rng.randint(0, 32, 128)] + 0.4 * rng.randn(128, 24)).astype(np.float32)
+    algo = A.get_algorithm_instance("Composite", 24, name="ivf", metric=metric,
+                                    indexer={"type": "FaissIVFIndexer", "index_type": "IVF64,Flat", "nprobe": 4},
+                                    searcher={"type": "FaissSearcher", "nprobe": 8})
+    algo.build_index(base)
+    index = algo.index_artifact.data
+    assert index.nprobe == 8 and index.ntotal == 20000 and algo.index_artifact.metadata["nprobe"] == 4
+    dist, idx = algo.batch_search(queries, 10)
+    # parity GIVEN the trained centroids and the device's assignment
+    b, q = (oracle.safe_normalize(base), oracle.safe_normalize(queries)) if metric == "cosine" else (base, queries)
+    m = "l2" if metric == "l2" else "ip"
+    ref_d, ref_i, _ = oracle.ivf_flat_search(b, index.centroids, index._impl.assign.cpu().numpy(), q, 10, 8, m)
+    got_d = dist if m == "l2" else -dist          # FaissSearcher negates ip / cosine scores (modular.py:545-546)
+    _check((ref_d, ref_i), (got_d, idx), atol=0.0 if m == "l2" else 1e-5)
+    gt = oracle.faiss_flat_search(b, q, 10, m)[1]
+    assert oracle.recall_at_k(gt, idx, 10) > 0.8
+    # legacy entry point, raw FAISS conventions
+    legacy = A.get_algorithm_instance("ApproximateSearch", 24, name="approx", index_type="IVF64,Flat", metric="l2", nprobe=64)
+    legacy.build_index(base)
+    d2, i2 = legacy.batch_search(queries, 10)
+    _check(oracle.faiss_flat_search(base, queries, 10, "l2"), (d2, i2))     # nprobe == nlist is exact
+    with pytest.raises(ValueError):
+        A.get_algorithm_instance("ApproximateSearch", 24, name="pq", index_type="IVF64,PQ8", metric="l2")
+
+
+def test_benchmark_runner_modular_end_to_end(A, tmp_path):
+    """reference tests/test_benchmark_runner_modular.py:9-65: a tiny JSON config through
+    BenchmarkRunner.run() with indexer_ref / searcher_ref resolution."""
+    from vectordb_retrieval_b200.harness import BenchmarkRunner
+    config = {
+        "output_dir": str(tmp_path / "out"),
+        "n_queries": 5, "topk": 5, "seed": 123, "query_batch_size": 2,
+        "indexers": {"bf": {"type": "BruteForceIndexer"}},
+        "searchers": {"linear": {"type": "LinearSearcher"}},
+        "algorithms": {"modular_exact": {"indexer_ref": "bf", "searcher_ref": "linear"},
+                       "exact": {"type": "ExactSearch"}},
+        "datasets": [{"name": "random", "metric": "l2",
+                      "dataset_options": {"dimensions": 3, "train_size": 32, "test_size": 6, "ground_truth_k": 5, "seed": 123}}],
+    }
+    path = tmp_path / "cfg.json"
+    path.write_text(json.dumps(config))
+    runner = BenchmarkRunner(str(path))
+    results = runner.run()
+    res = results["random"]["modular_exact"]
+    assert res["n_train"] == 32 and res["n_test"] == 5 and "recall@1" in res and res["recall@1"] == 1.0
+    assert results["random"]["exact"]["recall"] == 1.0
+    assert res["parameters"]["indexer"]["type"] == "BruteForceIndexer"
+    assert os.path.exists(os.path.join(runner.output_dir, "benchmark_summary.md"))
+    assert os.path.exists(os.path.join(runner.output_dir, "all_results.json"))
+
+
+def test_smoke_config_c1_through_cli_entry(A, tmp_path):
+    """BASELINE.json configs[0]: 10k x 128, 100 queries, ExactSearch k=10 via the smoke YAML."""
+    import yaml
+    from vectordb_retrieval_b200.harness import BenchmarkRunner
+    root = os.path.dirname(os.path.dirname(__file__))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "benchmark_config_smoke.yaml")))
+    cfg["output_dir"] = str(tmp_path / "out")
+    p = tmp_path / "smoke.yaml"
+    p.write_text(yaml.dump(cfg))
+    results = BenchmarkRunner(str(p)).run()["random"]
+    assert results["exact"]["recall@10"] == 1.0 and results["exact"]["recall@1"] == 1.0
+    assert results["exact_linear"]["recall@10"] == 1.0
+    assert 0.3 < results["ivf_flat"]["recall@10"] <= 1.0
+    assert results["faiss_lsh"]["recall@10"] > 0.5 and 0.0 < results["lsh"]["recall@10"] < 1.0
+    assert results["exact"]["n_train"] == 10000 and results["exact"]["n_test"] == 100

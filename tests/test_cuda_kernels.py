@@ -201,3 +201,51 @@ def test_row_utilities(eng):
     y = eng.normalize_rows_(x.clone()).cpu().numpy()
     np.testing.assert_allclose(y, oracle.safe_normalize(base), rtol=1e-6, atol=1e-7)
     assert (y[3] == 0).all()
+
+
+@pytest.mark.parametrize("n,d,nbits,nq,k", [(5000, 50, 256, 70, 100), (100000, 32, 256, 33, 1000), (3000, 16, 64, 9, 3000),
+                                            (70000, 24, 320, 17, 500), (400, 8, 1000, 5, 64)])
+def test_lsh_codes_and_hamming_topk_match_oracle(eng, n, d, nbits, nq, k):
+    """Sign codes equal the oracle's except on bits whose projection is within rounding of 0; the
+    Hamming top-k over the device's own codes is exactly the oracle's (distance, id) order."""
+    base, q = _data(n, d, nq, seed=n + nbits)
+    proj = np.random.RandomState(1234).normal(size=(nbits, d)).astype(np.float32)
+    shard = eng.HammingShard(base, proj, "cuda")
+    native = (nbits + 127) // 128 * 4
+    codes = shard.codes.cpu().numpy().view(np.uint32)
+    ref_codes, dots = oracle.lsh_sign_codes(base, proj)
+    assert (codes[:, native:] == 0).all()
+    diff = np.unpackbits((codes[:, :native] ^ ref_codes).view(np.uint8), axis=1, bitorder="little")[:, :nbits]
+    scale = np.abs(base).astype(np.float64) @ np.abs(proj).astype(np.float64).T
+    assert (np.abs(dots[diff.astype(bool)]) <= 1e-6 * scale[diff.astype(bool)]).all()
+    assert diff.mean() < 1e-4
+    qd = torch.from_numpy(q).cuda()
+    D, I = shard.search(qd, k)
+    qcodes = shard.encode(qd).cpu().numpy().view(np.uint32)
+    ref_d, ref_i = oracle.hamming_topk(codes, qcodes, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), ref_i)
+    np.testing.assert_array_equal(D.cpu().numpy(), ref_d)
+
+
+def test_faiss_lsh_pipeline_recall(eng):
+    """FaissLSHIndexer + FaissSearcher rerank through the public classes: rerank over Hamming
+    candidates equals the oracle's rerank over the same candidates; recall rises with the budget."""
+    import vectordb_retrieval_b200.algorithms as A
+    rng = np.random.RandomState(8)
+    centers = rng.randn(40, 32).astype(np.float32)
+    base = (centers[rng.randint(0, 40, 30000)] + 0.5 * rng.randn(30000, 32)).astype(np.float32)
+    queries = (centers[rng.randint(0, 40, 64)] + 0.5 * rng.randn(64, 32)).astype(np.float32)
+    gt = oracle.linear_search(base, queries, 10, "l2")[1]
+    recalls = []
+    for mult in (2.0, 32.0):
+        algo = A.get_algorithm_instance("Composite", 32, name="flsh", metric="l2",
+                                        indexer={"type": "FaissLSHIndexer", "num_bits": 256},
+                                        searcher={"type": "FaissSearcher", "lsh_candidate_multiplier": mult})
+        algo.build_index(base)
+        dist, idx = algo.batch_search(queries, 10)
+        index = algo.index_artifact.data
+        _, cand = index.search(queries, int(10 * mult))
+        ref = oracle.rerank_search(base, cand, queries, 10, "l2")
+        _check(ref, (dist, idx))
+        recalls.append(oracle.recall_at_k(gt, idx, 10))
+    assert recalls[1] > recalls[0] and recalls[1] > 0.6

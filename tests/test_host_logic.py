@@ -1,0 +1,156 @@
+"""CPU tests of the host-side logic: registries and YAML resolution, the LSH hashing / candidate
+ordering against the oracle (which is pinned to the reference), the shard plan, and the
+sharded search plumbing under torch.distributed with the gloo backend (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from oracle.gen_golden import random20k_inputs
+
+
+def test_registries_mirror_reference_type_names():
+    import vectordb_retrieval_b200.algorithms as A
+    for name in ("ExactSearch", "ApproximateSearch", "LSH", "Composite", "CompositeAlgorithm", "Modular"):
+        assert name in A.ALGORITHM_REGISTRY
+    for name in ("BruteForceIndexer", "FaissFactoryIndexer", "FaissIVFIndexer", "FaissLSHIndexer", "LSHIndexer"):
+        assert A.get_indexer_class(name).__name__ == name
+    for name in ("LinearSearcher", "FaissSearcher", "LSHSearcher"):
+        assert A.get_searcher_class(name).__name__ == name
+    with pytest.raises(ValueError):
+        A.get_indexer_class("HNSWIndexer")
+    with pytest.raises(ValueError):
+        A.FaissFactoryIndexer("x", 8, index_key="IVF16,PQ4")
+    with pytest.raises(ValueError):
+        A.LSHIndexer("x", 8, metric="ip")
+    with pytest.raises(ValueError):
+        A.LSHSearcher("x", 8, candidate_multiplier=0)
+    algo = A.get_algorithm_instance("Composite", 8, name="c", metric="cosine", indexer={"type": "BruteForceIndexer"},
+                                    searcher={"type": "LinearSearcher"})
+    assert algo.config["indexer"]["metric"] == "cosine" and algo.config["searcher"]["type"] == "LinearSearcher"
+    with pytest.raises(RuntimeError):
+        algo.batch_search(np.zeros((1, 8), dtype=np.float32), 1)
+    assert isinstance(algo, A.BaseAlgorithm)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import vectordb_retrieval_b200.algorithms as A
+    algo = A.get_algorithm_instance("ExactSearch", 4, name="e")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        algo.build_index(np.zeros((10, 4), dtype=np.float32))
+
+
+def test_yaml_component_resolution(tmp_path):
+    import yaml
+    from vectordb_retrieval_b200.harness import BenchmarkRunner
+    cfg = {"output_dir": str(tmp_path), "indexers": {"ivf": {"type": "FaissIVFIndexer", "index_type": "IVF100,Flat", "nprobe": 10}},
+           "searchers": {"faiss": {"type": "FaissSearcher"}},
+           "algorithms": {"a": {"indexer_ref": "ivf", "searcher_ref": "faiss", "indexer": {"nprobe": 32}}}, "datasets": []}
+    p = tmp_path / "c.yaml"
+    p.write_text(yaml.dump(cfg))
+    r = BenchmarkRunner(str(p))
+    algs = r._algorithms_for({"b": {"type": "ExactSearch"}}, "cosine")
+    assert algs["a"]["type"] == "Composite" and algs["a"]["indexer"] == {"type": "FaissIVFIndexer", "index_type": "IVF100,Flat", "nprobe": 32}
+    assert algs["a"]["metric"] == "cosine" and algs["b"]["metric"] == "cosine"
+    with pytest.raises(ValueError):
+        r._materialize_component("nope", None, r.global_indexers, "indexer")
+
+
+def test_lsh_tables_and_candidate_order_match_oracle():
+    from vectordb_retrieval_b200.algorithms.lsh import LSHIndexer, LSHSearcher
+    base, queries, _ = random20k_inputs()
+    base, queries = base[:4000], queries[:40]
+    art = LSHIndexer("i", 64, "l2", num_tables=12, hash_size=4, bucket_width=20.0, seed=42).build(base)
+    ref = oracle.LSHTables(base, "l2", 12, 4, 20.0, 42)
+    for t in range(12):
+        assert set(art.data["tables"][t]) == set(ref.tables[t])
+        for key, rows in ref.tables[t].items():
+            assert list(art.data["tables"][t][key]) == rows
+    s = LSHSearcher("s", 64, "l2", candidate_multiplier=8.0, fallback_to_bruteforce=False)
+    s.tables, s.projections, s.offsets, s.bit_weights = (art.data[k] for k in ("tables", "projections", "offsets", "bit_weights"))
+    s.metric, s.normalize_queries, s.hash_size, s.num_tables, s.bucket_width = "l2", False, 4, 12, 20.0
+    q = s._prepare_queries(queries)
+    for r, keys in enumerate(s._hash_queries(q)):
+        np.testing.assert_array_equal(s._ordered_candidates(keys)[: s._cap(20)],
+                                      oracle.lsh_candidates(ref, q[r], 20, 8.0, None, False))
+
+
+def test_shard_plan():
+    from vectordb_retrieval_b200.sharded import ShardPlan
+    p = ShardPlan(10, 4)
+    assert p.bounds() == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [p.owner(r) for r in (0, 2, 3, 9)] == [0, 0, 1, 3]
+    assert ShardPlan(3, 8).bounds()[3:] == [(3, 3)] * 5
+    assert sum(b - a for a, b in ShardPlan(1_000_000, 8).bounds()) == 1_000_000
+    with pytest.raises(ValueError):
+        ShardPlan(5, 0)
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import torch
+    import torch.distributed as dist
+    from vectordb_retrieval_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(0)
+    base = rng.randn(3001, 16).astype(np.float32)
+    queries = rng.randn(37, 16).astype(np.float32)
+    plan = sharded.ShardPlan(base.shape[0], world)
+    lo, hi = plan.start(rank), plan.stop(rank)
+
+    def local_search(q, k):                      # stands in for the CUDA shard: oracle on this rank's rows
+        d, i = oracle.faiss_flat_search(base[lo:hi], q, k, "l2")
+        i = np.where(i >= 0, i + lo, -1)
+        return torch.from_numpy(d), torch.from_numpy(i)
+
+    def merge(d_all, i_all):                     # stands in for vdb_merge_topk
+        d, i = oracle.merge_topk([x.numpy() for x in d_all], [x.numpy() for x in i_all], d_all.shape[2])
+        return torch.from_numpy(d), torch.from_numpy(i)
+
+    assert sharded.dist_info() == (rank, world)
+    d, i = sharded.ShardedTopK(local_search, sharded.allgather_topk, merge).search(queries, 25)
+    np.save(os.path.join(out_dir, f"d{rank}.npy"), d.numpy())
+    np.save(os.path.join(out_dir, f"i{rank}.npy"), i.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_search_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.RandomState(0)
+    base = rng.randn(3001, 16).astype(np.float32)
+    queries = rng.randn(37, 16).astype(np.float32)
+    ref_d, ref_i = oracle.faiss_flat_search(base, queries, 25, "l2")
+    for rank in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"i{rank}.npy"), ref_i)
+        np.testing.assert_allclose(np.load(tmp_path / f"d{rank}.npy"), ref_d, rtol=1e-6)
+
+
+def test_reference_registry_plugin_if_reference_present():
+    """the CUDA classes register into the reference's own registries."""
+    if not os.path.isdir("/root/reference/src/algorithms"):
+        pytest.skip("reference tree not present (GPU box)")
+    from vectordb_retrieval_b200 import plugin
+    mods = plugin.import_reference("/root/reference")
+    plugin.install(mods)
+    ref_algorithms, ref_modular = mods["algorithms"], mods["modular"]
+    import vectordb_retrieval_b200.algorithms as A
+    assert ref_algorithms.ALGORITHM_REGISTRY["ExactSearch"] is A.ExactSearch
+    assert ref_modular.SEARCHER_REGISTRY["LinearSearcher"] is A.LinearSearcher
+    algo = ref_algorithms.get_algorithm_instance("ExactSearch", 8, name="e", metric="l2")
+    assert isinstance(algo, ref_algorithms.BaseAlgorithm)          # the harness' isinstance check passes
+    comp = ref_algorithms.get_algorithm_instance("Composite", 8, name="c", indexer={"type": "BruteForceIndexer"},
+                                                 searcher={"type": "LinearSearcher"})
+    assert isinstance(comp.searcher, A.LinearSearcher)

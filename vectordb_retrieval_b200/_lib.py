@@ -24,6 +24,9 @@ _p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_
 SIGNATURES = {
     "vdb_last_error": (C.c_char_p, []),
     "vdb_abi_version": (_i32, []),
+    "vdb_launch_count": (_i64, []),
+    "vdb_flat_timing_enable": (_i32, [_i32]),
+    "vdb_flat_timing_read": (_i32, [C.POINTER(C.c_float), _i32, C.POINTER(C.c_int)]),
     "vdb_sm_count": (_i32, [C.POINTER(C.c_int)]),
     "vdb_row_norms": (_i32, [_p, _i64, _i32, _i64, _p, _p]),
     "vdb_normalize_rows": (_i32, [_p, _i64, _i32, _i64, _p, _i64, _p]),
@@ -39,8 +42,13 @@ SIGNATURES = {
     "vdb_set_debug_mode": (_i32, [_i32]),
     "vdb_merge_topk": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_rerank_topk": (_i32, [_i32, _p, _i64, _i32, _i64, _p, _i64, _i32, _p, _i64, _i32, _i32, _f32, _p, _p, _p]),
+    "vdb_lsh_code_words": (_i32, [_i32]),
+    "vdb_lsh_encode": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p]),
+    "vdb_hamming_topk_workspace_bytes": (_sz, [_i64, _i32]),
+    "vdb_hamming_topk": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "vdb_ivf_d4": (_i32, [_i32]),
     "vdb_ivf_count": (_i32, [_p, _i64, _i32, _p, _p]),
+    "vdb_kmeans_accumulate": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p, _p]),
     "vdb_ivf_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _i32, _p, _p, _p, _p]),
     "vdb_ivf_scan_topk": (_i32, [_i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
                                  _p, _p, _p, _p]),

@@ -11,6 +11,7 @@ namespace vdb {
 // ---------------------------------------------------------------------------------------------
 // error plumbing (host)
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // every kernel launched by the library is counted (vdb_launch_count)
 #define VDB_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

@@ -64,10 +64,17 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static int g_debug_mode = 0;
 
+// bench.py's roofline leg: scan-kernel durations measured with CUDA events on the launching stream
+constexpr int kTimingSlots = 512;
+static bool g_timing_on = false;
+static int g_timing_n = 0;
+static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
+static bool g_ev_made = false;
+
 // --------------------------------------------------------------------------------------------
-__global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt) {
+__global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int keep_thr) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < nq_pad) thr[i] = f2ord(CUDART_INF_F);
+  if (i < nq_pad && !keep_thr) thr[i] = f2ord(CUDART_INF_F);
   if (i < n_cnt) pool_cnt[i] = 0;
 }
 
@@ -405,10 +412,15 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
   P.dense = dense; P.dense_ld = n_pad; P.dbg = g_debug_mode;
   const int64_t n_cnt = nq_pad * plan.n_chunks;
-  flat_init_kernel<<<static_cast<unsigned>((n_cnt + 255) / 256), 256, 0, stream>>>(P.thr, nq_pad, P.pool_cnt, n_cnt);
+  flat_init_kernel<<<static_cast<unsigned>((n_cnt + 255) / 256), 256, 0, stream>>>(P.thr, nq_pad, P.pool_cnt, n_cnt,
+                                                                                      g_debug_mode == 5);
   VDB_CHECK_CUDA(cudaGetLastError());
+  const bool timed = g_timing_on && g_timing_n < kTimingSlots;
+  if (timed) VDB_CHECK_CUDA(cudaEventRecord(g_ev0[g_timing_n], stream));
   const int rc = run_scan<KP>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, plan, P, sm, stream);
   if (rc) return rc;
+  if (timed) VDB_CHECK_CUDA(cudaEventRecord(g_ev1[g_timing_n++], stream));
+  count_launches(2 + (out_d != nullptr ? 1 : 0));
   if (out_d != nullptr) {
     flat_finalize_kernel<KP><<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
         metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, plan.n_chunks, P.pools, P.pool_cnt, k, flags, pad_value,
@@ -428,6 +440,30 @@ int vdb_set_debug_mode(int mode) {
   const int old = g_debug_mode;
   g_debug_mode = mode;
   return old;
+}
+
+int vdb_flat_timing_enable(int on) {
+  if (on && !g_ev_made) {
+    for (int i = 0; i < kTimingSlots; ++i) {
+      VDB_CHECK_CUDA(cudaEventCreate(&g_ev0[i]));
+      VDB_CHECK_CUDA(cudaEventCreate(&g_ev1[i]));
+    }
+    g_ev_made = true;
+  }
+  g_timing_on = on != 0;
+  g_timing_n = 0;
+  return 0;
+}
+
+int vdb_flat_timing_read(float* ms, int max_records, int* n_out) {
+  const int n = g_timing_n < max_records ? g_timing_n : max_records;
+  for (int i = 0; i < n; ++i) {
+    VDB_CHECK_CUDA(cudaEventSynchronize(g_ev1[i]));
+    VDB_CHECK_CUDA(cudaEventElapsedTime(ms + i, g_ev0[i], g_ev1[i]));
+  }
+  if (n_out != nullptr) *n_out = n;
+  g_timing_n = 0;
+  return 0;
 }
 
 size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
@@ -495,6 +531,7 @@ int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t 
     case 256: merge_topk_kernel<256><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
     default: merge_topk_kernel<512><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
   }
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

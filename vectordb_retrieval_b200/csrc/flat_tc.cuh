@@ -37,7 +37,7 @@ struct FlatScanParams {
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
   float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
   int64_t dense_ld;
-  int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld
+  int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 6 drop full pools instead of compacting
 };
 
 namespace tc {
@@ -296,12 +296,12 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           // chunk c is in flight in va: wait, start chunk c+1 into vb, filter va under that latency
           tmem_ld_wait();
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
+          if (P.dbg == 6) { if (cnt > CAP - 32) cnt = 0; } else pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
           consume(va, c);
           tmem_ld_wait();
           if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, va);
           else release_tmem();
-          pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
+          if (P.dbg == 6) { if (cnt > CAP - 32) cnt = 0; } else pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
           consume(vb, c + 1);
         }
         __syncwarp();                              // all lanes are done with this tile's norms

@@ -39,6 +39,18 @@ __global__ void ivf_fill_kernel(const float* __restrict__ x, int64_t n, int d, i
   if (lane == 0) ids[b * 32 + v] = static_cast<int32_t>(row);
 }
 
+// k-means centroid update: sums[l, :] += x[row, :], counts[l] += 1 for l = assign[row]; one warp per row.
+__global__ void kmeans_accumulate_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
+                                         const int64_t* __restrict__ assign, int nlist, float* sums, int32_t* counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const int64_t l = assign[row];
+  if (l < 0 || l >= nlist) return;
+  for (int j = lane; j < d; j += 32) atomicAdd(sums + l * d + j, x[row * ld + j]);
+  if (lane == 0) atomicAdd(counts + l, 1);
+}
+
 template <int KP, int W>
 __global__ void __launch_bounds__(W * 32)
 ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __restrict__ ids,
@@ -103,6 +115,7 @@ static int launch_scan(int metric, const float* vecs, const int32_t* ids, const 
   kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(
       metric, reinterpret_cast<const float4*>(vecs), ids, blk_off, nlist, d4, probes, nprobe, q, ld_q, d, k, flags,
       pad_value, id_offset, out_d, out_i, reinterpret_cast<unsigned long long*>(scanned));
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -118,6 +131,17 @@ int vdb_ivf_d4(int d) { return (d + 3) / 4; }
 int vdb_ivf_count(const int32_t* assign, int64_t n, int nlist, int32_t* counts, void* stream) {
   VDB_REQUIRE(n > 0 && nlist > 0, "vdb_ivf_count: bad shape");
   ivf_count_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(assign, n, nlist, counts);
+  count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vdb_kmeans_accumulate(const float* x, int64_t n, int d, int64_t ld, const int64_t* assign, int nlist, float* sums,
+                          int32_t* counts, void* stream) {
+  VDB_REQUIRE(n > 0 && d > 0 && ld >= d && nlist > 0, "vdb_kmeans_accumulate: bad shape");
+  kmeans_accumulate_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, d, ld, assign, nlist, sums, counts);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -127,6 +151,7 @@ int vdb_ivf_fill(const float* x, int64_t n, int d, int64_t ld, const int32_t* as
   VDB_REQUIRE(n > 0 && n < (int64_t(1) << 31) && d > 0 && ld >= d && nlist > 0, "vdb_ivf_fill: bad shape");
   ivf_fill_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, n, d, ld, assign, blk_off, nlist, cursor, list_vecs, list_ids);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,317 @@
+// Sign-projection codes and Hamming top-k: the candidate generator in front of the LSH rerank.
+//   reference: faiss.IndexLSH(d, nbits).add / .search reached from
+//   src/algorithms/modular.py:215-216 (FaissLSHIndexer.build) and :477 (candidate search).
+//
+// Hamming distances are small integers, so selection is a counting problem, not a sort:
+//   1. count   per query, a histogram of the distances <= a bound T (bound from a row sample, so
+//              almost every row fails one compare and touches nothing)
+//   2. cut     smallest distance t* whose cumulative count reaches k, the number r of rows to take
+//              from bin t*, and the output offset of every bin
+//   3. emit    second pass in row order: rows below t* and the first r rows of bin t* are written
+//              at offset[bin] + rank - a stable counting sort, so the output is ordered by
+//              (distance, id) without sorting anything.
+// One warp owns QT queries (codes in registers) and streams the row codes with 128-bit loads, one
+// row per lane; there is no inter-warp communication, hence the row order and the result are
+// deterministic.  Integer / byte work: bound by the popc + compare issue rate and L2 bandwidth.
+#include "common.cuh"
+
+namespace vdb {
+
+// ---------------------------------------------------------------------------------------------
+// codes[row, w] bit b = [ sum_j x[row, j] * projT[j, w*32 + b] >= 0 ]; one warp per row, lane = bit.
+__global__ void lsh_encode_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld,
+                                  const float* __restrict__ projT /* [d][nbits_pad] */, int nbits, int nbits_pad,
+                                  uint32_t* __restrict__ codes /* [n][nbits_pad / 32] */) {
+  extern __shared__ float xs[];   // [warps][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= n) return;
+  float* xr = xs + warp * d;
+  for (int j = lane; j < d; j += 32) xr[j] = x[row * ld + j];
+  __syncwarp();
+  const int words = nbits_pad >> 5;
+  for (int w = 0; w < words; ++w) {
+    const int b = w * 32 + lane;
+    float acc = 0.f;
+    for (int j = 0; j < d; ++j) acc = fmaf(xr[j], __ldg(projT + static_cast<int64_t>(j) * nbits_pad + b), acc);
+    const unsigned word = __ballot_sync(0xffffffffu, b < nbits && acc >= 0.f);
+    if (lane == 0) codes[row * words + w] = word;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int W4>
+__device__ __forceinline__ int hamming(const uint4 (&a)[W4], const uint4 (&b)[W4]) {
+  int dist = 0;
+#pragma unroll
+  for (int w = 0; w < W4; ++w) {
+    const unsigned long long x0 = (static_cast<unsigned long long>(a[w].x ^ b[w].x) << 32) | (a[w].y ^ b[w].y);
+    const unsigned long long x1 = (static_cast<unsigned long long>(a[w].z ^ b[w].z) << 32) | (a[w].w ^ b[w].w);
+    dist += __popcll(x0) + __popcll(x1);
+  }
+  return dist;
+}
+
+template <int W4>
+constexpr int queries_per_warp() { return W4 <= 2 ? 8 : (W4 == 4 ? 4 : 2); }
+
+// Histogram of the distances <= T[q] over rows [row_begin, row_end).  T == nullptr: every distance.
+// `only` (nullable): process just the flagged queries.
+template <int W4>
+__global__ void __launch_bounds__(128)
+hamming_count_kernel(const uint4* __restrict__ codes, int64_t row_begin, int64_t row_end, const uint4* __restrict__ qcodes,
+                     int64_t nq, int nbits, const int* __restrict__ T, const uint8_t* __restrict__ only,
+                     int* __restrict__ hist /* [nq][nbits + 1] */) {
+  constexpr int QT = queries_per_warp<W4>();
+  extern __shared__ int smem_i[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bins = nbits + 1;
+  const int64_t q0 = (static_cast<int64_t>(blockIdx.x) * 4 + warp) * QT;
+  if (q0 >= nq) return;
+  int* h = smem_i + warp * QT * bins;
+  for (int i = lane; i < QT * bins; i += 32) h[i] = 0;
+  uint4 qc[QT][W4];
+  int tq[QT];
+  bool any = false;
+#pragma unroll
+  for (int qi = 0; qi < QT; ++qi) {
+    const int64_t q = q0 + qi;
+    const bool live = q < nq && (only == nullptr || only[q] != 0);
+    tq[qi] = live ? (T != nullptr ? T[q] : nbits) : -1;
+    any |= live;
+#pragma unroll
+    for (int w = 0; w < W4; ++w) qc[qi][w] = live ? qcodes[q * W4 + w] : make_uint4(0, 0, 0, 0);
+  }
+  if (!any) return;
+  __syncwarp();
+  for (int64_t row0 = row_begin; row0 < row_end; row0 += 32) {
+    const int64_t row = row0 + lane;
+    const bool valid = row < row_end;
+    uint4 c[W4];
+#pragma unroll
+    for (int w = 0; w < W4; ++w) c[w] = valid ? __ldg(codes + row * W4 + w) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+      const int dist = hamming<W4>(c, qc[qi]);
+      if (valid && dist <= tq[qi]) atomicAdd(h + qi * bins + dist, 1);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int qi = 0; qi < QT; ++qi) {
+    if (tq[qi] >= 0) {
+      for (int b = lane; b < bins; b += 32) hist[(q0 + qi) * bins + b] = h[qi * bins + b];
+    }
+  }
+}
+
+// Bound from a sample of `s` rows: smallest t whose sample count, scaled to n rows, covers k with
+// a 25% margin.  An estimate only - the cut kernel verifies it and asks for a recount if short.
+__global__ void hamming_bound_kernel(const int* __restrict__ hist, int64_t nq, int nbits, int64_t s, int64_t n, int k,
+                                     int* __restrict__ T) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int bins = nbits + 1;
+  const double need = (1.25 * k + 16.0) * static_cast<double>(s) / static_cast<double>(n);
+  long long cum = 0;
+  int t = nbits;
+  for (int b = 0; b < bins; ++b) {
+    cum += hist[q * bins + b];
+    if (static_cast<double>(cum) >= need) { t = b; break; }
+  }
+  T[q] = t;
+}
+
+// hist -> (cut bin, rows to take from it, exclusive prefix written back into hist).  A query whose
+// bound turned out too small (fewer than k rows counted) is flagged for a full recount.
+__global__ void hamming_cut_kernel(int* __restrict__ hist, int64_t nq, int nbits, int k, int* __restrict__ T,
+                                   const uint8_t* __restrict__ only, int* __restrict__ cut, int* __restrict__ take,
+                                   uint8_t* __restrict__ redo) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  if (only != nullptr && only[q] == 0) { if (redo != nullptr) redo[q] = 0; return; }
+  const int bins = nbits + 1;
+  const int bound = T != nullptr ? T[q] : nbits;
+  long long cum = 0;
+  int t = -1;
+  for (int b = 0; b <= bound; ++b) {
+    const int c = hist[q * bins + b];
+    hist[q * bins + b] = static_cast<int>(cum);      // exclusive prefix = output offset of bin b
+    if (t < 0 && cum + c >= k) { t = b; take[q] = static_cast<int>(k - cum); }
+    cum += c;
+  }
+  if (t < 0) {
+    if (bound < nbits && redo != nullptr) {            // the estimate was too tight: count everything
+      redo[q] = 1;
+      T[q] = nbits;
+      cut[q] = -1;
+      take[q] = 0;
+      return;
+    }
+    t = nbits + 1;                                     // fewer than k rows exist: take them all
+    take[q] = 0;
+  }
+  cut[q] = t;
+  if (redo != nullptr) redo[q] = 0;
+}
+
+// Emission in row order.  offs = hist after the cut kernel (exclusive prefix per bin).
+template <int W4>
+__global__ void __launch_bounds__(128)
+hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, const uint4* __restrict__ qcodes, int64_t nq, int nbits,
+                    const int* __restrict__ cut, const int* __restrict__ take, const int* __restrict__ offs, int k,
+                    int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  constexpr int QT = queries_per_warp<W4>();
+  extern __shared__ int smem_i[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int bins = nbits + 1;
+  const int64_t q0 = (static_cast<int64_t>(blockIdx.x) * 4 + warp) * QT;
+  if (q0 >= nq) return;
+  int* cursor = smem_i + warp * QT * bins;
+  uint4 qc[QT][W4];
+  int cq[QT], rq[QT], seen[QT];
+#pragma unroll
+  for (int qi = 0; qi < QT; ++qi) {
+    const int64_t q = q0 + qi;
+    const bool live = q < nq;
+    cq[qi] = live ? cut[q] : -1;
+    rq[qi] = live ? take[q] : 0;
+    seen[qi] = 0;
+    for (int b = lane; b < bins; b += 32) cursor[qi * bins + b] = live ? offs[q * bins + b] : 0;
+#pragma unroll
+    for (int w = 0; w < W4; ++w) qc[qi][w] = live ? qcodes[q * W4 + w] : make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  for (int64_t row0 = 0; row0 < n; row0 += 32) {
+    const int64_t row = row0 + lane;
+    const bool valid = row < n;
+    uint4 c[W4];
+#pragma unroll
+    for (int w = 0; w < W4; ++w) c[w] = valid ? __ldg(codes + row * W4 + w) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+      const int dist = hamming<W4>(c, qc[qi]);
+      const bool below = valid && dist < cq[qi];
+      const bool tie = valid && dist == cq[qi];
+      const unsigned tie_m = __ballot_sync(0xffffffffu, tie);
+      const bool takes = below || (tie && seen[qi] + __popc(tie_m & lt_mask) < rq[qi]);
+      seen[qi] += __popc(tie_m);
+      const unsigned take_m = __ballot_sync(0xffffffffu, takes);
+      if (take_m == 0u) continue;
+      int peers_n = 0, rank = 0, slot = 0;
+      if (takes) {
+        const unsigned peers = __match_any_sync(take_m, dist);
+        rank = __popc(peers & lt_mask);
+        peers_n = __popc(peers);
+        slot = cursor[qi * bins + dist] + rank;
+        if (slot < k) {
+          out_d[(q0 + qi) * k + slot] = static_cast<float>(dist);
+          out_i[(q0 + qi) * k + slot] = row + id_offset;
+        }
+      }
+      __syncwarp();
+      if (takes && rank == 0) cursor[qi * bins + dist] += peers_n;
+      __syncwarp();
+    }
+  }
+}
+
+template <int W4>
+static int run_hamming(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                       int64_t id_offset, float* out_d, int64_t* out_i, void* ws, cudaStream_t s) {
+  constexpr int QT = queries_per_warp<W4>();
+  const int bins = nbits + 1;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  int* hist = reinterpret_cast<int*>(w);
+  size_t off = (static_cast<size_t>(nq) * bins * 4 + 255) & ~size_t(255);
+  int* T = reinterpret_cast<int*>(w + off);   off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
+  int* cut = reinterpret_cast<int*>(w + off); off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
+  int* take = reinterpret_cast<int*>(w + off); off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
+  uint8_t* redo = w + off;
+  const uint4* c4 = reinterpret_cast<const uint4*>(codes);
+  const uint4* q4 = reinterpret_cast<const uint4*>(qcodes);
+  const unsigned blocks = static_cast<unsigned>((nq + 4 * QT - 1) / (4 * QT));
+  const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
+  const size_t smem = static_cast<size_t>(4) * QT * bins * sizeof(int);
+  auto count = hamming_count_kernel<W4>;
+  auto emit = hamming_emit_kernel<W4>;
+  if (smem > 48 * 1024) {
+    VDB_CHECK_CUDA(cudaFuncSetAttribute(count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    VDB_CHECK_CUDA(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  constexpr int64_t kSample = 32768;
+  if (n <= 2 * kSample) {            // small base: one exact count
+    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, nullptr, nullptr, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, nullptr, nullptr, cut, take, nullptr);
+    count_launches(2);
+  } else {
+    count<<<blocks, 128, smem, s>>>(c4, 0, kSample, q4, nq, nbits, nullptr, nullptr, hist);
+    hamming_bound_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, kSample, n, k, T);
+    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, T, nullptr, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, T, nullptr, cut, take, redo);
+    // queries whose bound was short are recounted without a bound (warps without such a query exit at once)
+    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, T, redo, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, T, redo, cut, take, nullptr);
+    count_launches(6);
+  }
+  emit<<<blocks, 128, smem, s>>>(c4, n, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i);
+  count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" {
+
+int vdb_lsh_code_words(int nbits) { return (nbits + 127) / 128 * 4; }
+
+int vdb_lsh_encode(const float* x, int64_t n, int d, int64_t ld, const float* proj_t, int nbits, uint32_t* codes,
+                   void* stream) {
+  VDB_REQUIRE(n > 0 && d > 0 && ld >= d && nbits > 0 && nbits <= 1024, "vdb_lsh_encode: bad shape n=%lld d=%d nbits=%d",
+              (long long)n, d, nbits);
+  const int nbits_pad = vdb_lsh_code_words(nbits) * 32;
+  const int warps = 8;
+  const size_t smem = static_cast<size_t>(warps) * d * sizeof(float);
+  VDB_REQUIRE(smem <= 48 * 1024, "vdb_lsh_encode: d=%d too large", d);
+  lsh_encode_kernel<<<static_cast<unsigned>((n + warps - 1) / warps), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, n, d, ld, proj_t, nbits, nbits_pad, codes);
+  count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t vdb_hamming_topk_workspace_bytes(int64_t nq, int nbits) {
+  if (nq <= 0 || nbits <= 0) return 0;
+  const size_t a = (static_cast<size_t>(nq) * (nbits + 1) * 4 + 255) & ~size_t(255);
+  const size_t b = (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
+  return a + 3 * b + ((static_cast<size_t>(nq) + 255) & ~size_t(255));
+}
+
+int vdb_hamming_topk(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                     int64_t id_offset, float* out_d, int64_t* out_i, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  VDB_REQUIRE(n > 0 && nq > 0 && nbits > 0 && nbits <= 1024 && k >= 1, "vdb_hamming_topk: bad shape");
+  VDB_REQUIRE(workspace != nullptr && workspace_bytes >= vdb_hamming_topk_workspace_bytes(nq, nbits),
+              "vdb_hamming_topk: workspace too small");
+  VDB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0 && (reinterpret_cast<uintptr_t>(qcodes) & 15) == 0,
+              "vdb_hamming_topk: codes must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (vdb_lsh_code_words(nbits) / 4) {
+    case 1: return run_hamming<1>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace, s);
+    case 2: return run_hamming<2>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace, s);
+    case 3: case 4: {
+      VDB_REQUIRE(vdb_lsh_code_words(nbits) == 16, "vdb_hamming_topk: nbits in (256, 512] must be padded to 512 by the caller");
+      return run_hamming<4>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace, s);
+    }
+    default: {
+      VDB_REQUIRE(vdb_lsh_code_words(nbits) == 32, "vdb_hamming_topk: nbits in (512, 1024] must be padded to 1024 by the caller");
+      return run_hamming<8>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace, s);
+    }
+  }
+}
+
+}  // extern "C"

@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 // one warp per row; fp64 accumulation so the result is the correctly rounded |x|^2
 __global__ void row_norms_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -93,6 +97,7 @@ extern "C" {
 
 const char* vdb_last_error(void) { return vdb::last_error(); }
 int vdb_abi_version(void) { return VDB_ABI_VERSION; }
+int64_t vdb_launch_count(void) { return static_cast<int64_t>(vdb::launches()); }
 
 int vdb_sm_count(int* out) {
   int dev = 0;
@@ -106,6 +111,7 @@ int vdb_row_norms(const float* x, int64_t n, int d, int64_t ld, float* out, void
   if (n == 0) return 0;
   const int64_t blocks = (n * 32 + 255) / 256;
   row_norms_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, d, ld, out);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -115,6 +121,7 @@ int vdb_normalize_rows(const float* x, int64_t n, int d, int64_t ld, float* y, i
   if (n == 0) return 0;
   const int64_t blocks = (n * 32 + 255) / 256;
   normalize_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, d, ld, y, ld_y);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -131,6 +138,7 @@ int vdb_flat_prepare(const float* x, int64_t n, int d, int64_t ld, int metric, f
   const int64_t blocks = (n_pad * 32 + 255) / 256;
   split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, n, n_pad, d, ld, vdb_flat_kpad(d), metric, 1.f, hi, lo, norms);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -141,6 +149,7 @@ int vdb_flat_prepare_queries(const float* q, int64_t nq, int d, int64_t ld, floa
   const int64_t blocks = (nq_pad * 32 + 255) / 256;
   split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       q, nq, nq_pad, d, ld, vdb_flat_kpad(d), VDB_METRIC_IP, -2.f, q_hi, q_lo, nullptr);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -63,6 +63,7 @@ static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, c, q, ld_q, k, flags,
                                                              pad_value, out_d, out_i);
+  count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

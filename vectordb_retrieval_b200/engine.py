@@ -255,6 +255,68 @@ class Reranker:
         return out_d, out_i
 
 
+def kmeans_train(vectors, nlist: int, metric: str = "l2", device=None, niter: int = 10, seed: int = 1234,
+                 max_points_per_centroid: int = 256, batch: int = 1 << 18) -> np.ndarray:
+    """Lloyd k-means on the device for the IVF coarse quantiser; returns centroids [nlist, d] (host).
+
+    Follows the shape of FAISS's ``Clustering`` as reached through ``index.train``
+    (reference src/algorithms/modular.py:281-282): at most ``max_points_per_centroid * nlist``
+    training points sampled without replacement, ``niter`` iterations, random distinct rows as
+    initial centroids, empty clusters re-seeded by splitting the most populated one.  l2: nearest
+    centroid by L2; ip / cosine: spherical k-means (assignment by inner product, centroids
+    re-normalised).  FAISS's RNG stream is not reproduced (parity unpinned).
+    Assignment = the flat scan kernel with base := centroids, k := 1."""
+    lib = _lib.load()
+    dev = _require_cuda(device)
+    n, d = int(vectors.shape[0]), int(vectors.shape[1])
+    if n < nlist:
+        raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({nlist})")
+    rng = np.random.RandomState(seed)
+    limit = max_points_per_centroid * nlist
+    if n > limit:
+        rows = np.sort(rng.choice(n, limit, replace=False))
+        sample_host = np.ascontiguousarray(vectors[rows], dtype=np.float32)
+    else:
+        sample_host = vectors
+    with torch.cuda.device(dev):
+        sample = to_device_f32(sample_host, dev)
+        if metric == "cosine":
+            normalize_rows_(sample)
+        ns = sample.shape[0]
+        init = torch.from_numpy(np.sort(rng.permutation(ns)[:nlist])).to(dev)
+        cent = sample[init].clone()
+        qmetric = "l2" if metric == "l2" else "ip"
+        for _ in range(max(niter, 0)):
+            quant = FlatShard(cent, qmetric, dev)
+            sums = torch.zeros((nlist, d), dtype=torch.float32, device=dev)
+            counts = torch.zeros(nlist, dtype=torch.int32, device=dev)
+            for s in range(0, ns, batch):
+                blk = sample[s:s + batch]
+                _, idx = quant.search(blk.clone(), 1)
+                check(lib.vdb_kmeans_accumulate(ptr(blk), blk.shape[0], d, blk.stride(0), ptr(idx), nlist, ptr(sums),
+                                                ptr(counts), _stream(dev)), "vdb_kmeans_accumulate")
+            del quant
+            cnt_host = counts.cpu().numpy().astype(np.int64)
+            new = sums / counts.clamp(min=1).to(torch.float32)[:, None]
+            empty = np.nonzero(cnt_host == 0)[0]
+            if empty.size:                                   # split the biggest clusters (FAISS does the same)
+                new_host = new.cpu().numpy()
+                for j, e in enumerate(empty.tolist()):
+                    big = int(np.argmax(cnt_host))
+                    eps = 1.0 / 1024.0
+                    sign = np.where(np.arange(d) % 2 == 0, 1.0 + eps, 1.0 - eps).astype(np.float32)
+                    new_host[e] = new_host[big] * sign
+                    new_host[big] = new_host[big] * (2.0 - sign)
+                    cnt_host[e] = cnt_host[big] // 2
+                    cnt_host[big] -= cnt_host[e]
+                new = torch.from_numpy(new_host).to(dev)
+            if qmetric == "ip":
+                normalize_rows_(new)
+            cent = new
+        torch.cuda.current_stream(dev).synchronize()
+        return cent.cpu().numpy()
+
+
 class IVFShard:
     """IVF-Flat index of one GPU's rows: centroids as a FlatShard (coarse quantiser) plus the
     inverted lists in the interleaved-32 layout."""
@@ -314,4 +376,72 @@ class IVFShard:
                                              q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
                                              ptr(scanned), _stream(self.dev)), "vdb_ivf_scan_topk")
         self.last_probes = probes
+        return out_d, out_i
+
+
+class HammingShard:
+    """Sign-projection codes of one GPU's rows + the Hamming top-k scan (``faiss.IndexLSH``).
+
+    HBM layout: ``codes`` [n, words] int32 (words = 4 * ceil(nbits / 128), 32 bytes per row at 256
+    bits) and the transposed projection [d, words * 32]."""
+
+    def __init__(self, vectors, projection: np.ndarray, device=None, id_offset: int = 0, upload_rows: int = 1 << 20):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.id_offset = int(id_offset)
+        self.nbits, self.d = int(projection.shape[0]), int(projection.shape[1])
+        if vectors.shape[1] != self.d:
+            raise RuntimeError(f"expected dimension {self.d}, got {vectors.shape[1]}")
+        if self.nbits > 1024:
+            raise RuntimeError("at most 1024 hash bits are supported")
+        self.n = int(vectors.shape[0])
+        self.words = self.lib.vdb_lsh_code_words(self.nbits)
+        if self.words == 12:
+            self.words = 16            # (256, 512] bits share the 512-bit kernel
+        elif self.words > 16:
+            self.words = 32
+        with torch.cuda.device(self.dev):
+            pt = np.zeros((self.d, self.lib.vdb_lsh_code_words(self.nbits) * 32), dtype=np.float32)
+            pt[:, : self.nbits] = np.ascontiguousarray(projection, dtype=np.float32).T
+            self.proj_t = torch.from_numpy(pt).to(self.dev)
+            self.codes = torch.zeros((self.n, self.words), dtype=torch.int32, device=self.dev)
+            for s in range(0, self.n, upload_rows):
+                blk = to_device_f32(vectors[s:s + upload_rows], self.dev)
+                self._encode(blk, self.codes[s:s + blk.shape[0]])
+                del blk
+            torch.cuda.current_stream(self.dev).synchronize()
+
+    def _encode(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        native = self.lib.vdb_lsh_code_words(self.nbits)
+        if native == self.words:
+            check(self.lib.vdb_lsh_encode(ptr(x), x.shape[0], self.d, x.stride(0), ptr(self.proj_t), self.nbits, ptr(out),
+                                          _stream(self.dev)), "vdb_lsh_encode")
+        else:                                   # widen to the kernel's code width, padding words stay zero
+            tmp = torch.empty((x.shape[0], native), dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_lsh_encode(ptr(x), x.shape[0], self.d, x.stride(0), ptr(self.proj_t), self.nbits, ptr(tmp),
+                                          _stream(self.dev)), "vdb_lsh_encode")
+            out.zero_()
+            out[:, :native].copy_(tmp)
+
+    def memory_bytes(self) -> int:
+        return self.codes.numel() * 4 + self.proj_t.numel() * 4
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        out = torch.zeros((x.shape[0], self.words), dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self._encode(x.contiguous(), out)
+        return out
+
+    def search(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(Hamming distance as float32 [nq,k], ids int64 [nq,k]) ordered by (distance, id); k > n pads (inf, -1)."""
+        nq = q.shape[0]
+        nbits_kernel = self.words * 32 if self.words != self.lib.vdb_lsh_code_words(self.nbits) else self.nbits
+        with torch.cuda.device(self.dev):
+            qc = self.encode(q)
+            out_d = torch.full((nq, k), float("inf"), dtype=torch.float32, device=self.dev)
+            out_i = torch.full((nq, k), -1, dtype=torch.int64, device=self.dev)
+            nbytes = self.lib.vdb_hamming_topk_workspace_bytes(nq, nbits_kernel)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            check(self.lib.vdb_hamming_topk(ptr(self.codes), self.n, ptr(qc), nq, nbits_kernel, k, self.id_offset,
+                                            ptr(out_d), ptr(out_i), ptr(ws), nbytes, _stream(self.dev)), "vdb_hamming_topk")
         return out_d, out_i

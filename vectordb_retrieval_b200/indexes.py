@@ -1,0 +1,216 @@
+"""FAISS-shaped index objects backed by the CUDA kernels.
+
+The reference talks to FAISS through a small duck type - ``index.train(x)``, ``index.add(x)``,
+``index.search(q, k) -> (D, I)``, ``index.ntotal``, ``index.nprobe``, ``index.is_trained`` - from
+``faiss.IndexFlat`` (src/algorithms/exact_search.py:38-39,78), ``faiss.index_factory``
+(src/algorithms/modular.py:277-286, src/algorithms/approximate_search.py:39-51) and
+``faiss.IndexLSH`` (src/algorithms/modular.py:215-216,477).  These classes offer that duck type
+with FAISS's value conventions (squared L2 ascending, raw inner product descending, int64
+labels, -1 / +-FLT_MAX padding) so the reference-facing searchers can stay thin.
+
+Host arrays in, host arrays out; ``search_device`` keeps everything on the GPU for callers that
+chain kernels.  No CPU fallback: constructing any of these without a CUDA device raises."""
+from __future__ import annotations
+
+import re
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+METRIC_L2, METRIC_INNER_PRODUCT = 1, 0     # numeric values of faiss.METRIC_* (only used as tags)
+
+
+def _metric_name(metric) -> str:
+    if isinstance(metric, str):
+        return "l2" if metric == "l2" else "ip"
+    return "l2" if metric == METRIC_L2 else "ip"
+
+
+class GpuIndexFlat:
+    """``faiss.IndexFlat(d, metric)``: exact search on one GPU, or row-sharded over several."""
+
+    def __init__(self, d: int, metric="l2", device=None, devices=None, normalize: bool = False):
+        self.d = int(d)
+        self.metric = _metric_name(metric)
+        self.normalize = bool(normalize)      # cosine: rows and queries are L2-normalised on the device
+        self.device, self.devices = device, devices
+        self.is_trained = True
+        self.ntotal = 0
+        self._impl = None
+
+    def train(self, x) -> None:   # nothing to train
+        return None
+
+    def add(self, x) -> None:
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexFlat.add may be called once (the shard layout is built in one pass)")
+        if x.shape[1] != self.d:
+            raise RuntimeError(f"expected dimension {self.d}, got {x.shape[1]}")
+        from . import sharded
+        rank, world = sharded.dist_info()
+        metric = "cosine" if self.normalize and self.metric == "ip" else self.metric
+        if world > 1:
+            self._impl = sharded.DistributedFlatIndex.from_global(x, metric, self.device)
+        elif self.devices is not None and len(self.devices) > 1:
+            self._impl = sharded.MultiDeviceFlatIndex(x, metric, self.devices)
+        else:
+            dev = self.device if self.device is not None else (self.devices[0] if self.devices else None)
+            self._impl = engine.FlatShard(x, metric, dev)
+        self.ntotal = int(x.shape[0])
+
+    @property
+    def home(self) -> torch.device:
+        impl = self._impl
+        return impl.home if hasattr(impl, "home") else (impl.shard.dev if hasattr(impl, "shard") else impl.dev)
+
+    def memory_bytes(self) -> int:
+        return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+        return self._impl.search(q, k, 0, pad)
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        with torch.cuda.device(self.home):
+            q = engine.queries_to_device(queries, self.home, self.d)
+            return engine.results_to_host(*self.search_device(q, int(k)))
+
+
+class GpuIndexIVFFlat:
+    """``faiss.index_factory(d, "IVF<nlist>,Flat", metric)``: k-means coarse quantiser + inverted lists.
+
+    train  k-means (Lloyd, ``niter`` = 10 like FAISS's IVF default, at most 256 points per
+           centroid sampled with seed 1234), assignment by the flat kernel with base := centroids;
+           inner-product indexes use spherical k-means.  FAISS's own RNG / subsampling cannot be
+           reproduced without FAISS, so parity with FAISS is defined GIVEN the same centroids
+           (pass ``centroids=`` to skip training).
+    add    nearest-centroid assignment + scatter into the interleaved-32 list layout
+    search top-``nprobe`` centroids per query, scan of those lists with exact scoring."""
+
+    def __init__(self, d: int, nlist: int, metric="l2", device=None, niter: int = 10, seed: int = 1234,
+                 max_points_per_centroid: int = 256, centroids: Optional[np.ndarray] = None, normalize: bool = False):
+        if nlist <= 0:
+            raise ValueError("nlist must be positive")
+        self.d, self.nlist = int(d), int(nlist)
+        self.metric = _metric_name(metric)
+        self.normalize = bool(normalize)
+        self.device = device
+        self.niter, self.seed, self.max_points_per_centroid = int(niter), int(seed), int(max_points_per_centroid)
+        self.nprobe = 1
+        self.ntotal = 0
+        self.centroids = None if centroids is None else np.ascontiguousarray(centroids, dtype=np.float32)
+        self.is_trained = self.centroids is not None
+        self._impl: Optional[engine.IVFShard] = None
+
+    def train(self, x) -> None:
+        if self.is_trained:
+            return
+        self.centroids = engine.kmeans_train(x, self.nlist, self._engine_metric(), self.device, niter=self.niter, seed=self.seed,
+                                             max_points_per_centroid=self.max_points_per_centroid)
+        self.is_trained = True
+
+    def _engine_metric(self) -> str:
+        return "cosine" if self.normalize and self.metric == "ip" else self.metric
+
+    def add(self, x) -> None:
+        if not self.is_trained:
+            raise RuntimeError("GpuIndexIVFFlat.add before train")
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexIVFFlat.add may be called once")
+        self._impl = engine.IVFShard(x, self.centroids, self._engine_metric(), self.device)
+        self.ntotal = int(x.shape[0])
+
+    @property
+    def home(self) -> torch.device:
+        return self._impl.dev
+
+    def memory_bytes(self) -> int:
+        return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+        return self._impl.search(q, k, int(self.nprobe), 0, pad)
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        with torch.cuda.device(self.home):
+            q = engine.queries_to_device(queries, self.home, self.d)
+            return engine.results_to_host(*self.search_device(q, int(k)))
+
+
+class GpuIndexLSH:
+    """``faiss.IndexLSH(d, nbits)``: sign bits of a random projection, Hamming top-k.
+
+    Codes: bit b of row x = [ (x @ P)[b] >= 0 ], P a d x nbits Gaussian matrix from
+    ``RandomState(seed)`` (FAISS draws its own rotation with its own RNG - parity with FAISS's
+    codes is unpinned, the candidate *rerank* that follows is what the reference's results hinge
+    on).  search returns (Hamming distance as float32, ids) ordered by (distance, id)."""
+
+    def __init__(self, d: int, nbits: int, device=None, seed: int = 1234, projection: Optional[np.ndarray] = None):
+        if nbits <= 0:
+            raise ValueError("num_bits must be positive")
+        self.d, self.nbits = int(d), int(nbits)
+        self.device = device
+        self.is_trained = True
+        self.ntotal = 0
+        if projection is None:
+            projection = np.random.RandomState(seed).normal(size=(self.nbits, self.d)).astype(np.float32)
+        self.projection = np.ascontiguousarray(projection, dtype=np.float32)   # [nbits, d]
+        self._impl: Optional[engine.HammingShard] = None
+
+    def train(self, x) -> None:
+        return None
+
+    def add(self, x) -> None:
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexLSH.add may be called once")
+        self._impl = engine.HammingShard(x, self.projection, self.device)
+        self.ntotal = int(x.shape[0])
+
+    @property
+    def home(self) -> torch.device:
+        return self._impl.dev
+
+    def memory_bytes(self) -> int:
+        return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        return self._impl.search(q, int(k))
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        with torch.cuda.device(self.home):
+            q = engine.queries_to_device(queries, self.home, self.d)
+            d, i = self.search_device(q, int(k))
+            return engine.results_to_host(d.to(torch.float32), i)
+
+
+_IVF_FLAT = re.compile(r"^IVF(\d+),Flat$")
+
+
+def index_factory(d: int, key: str, metric="l2", **kwargs):
+    """The subset of ``faiss.index_factory`` grammar that reaches the scan + top-k path:
+    ``"Flat"``, ``"IVF<nlist>,Flat"`` and ``"LSH"``.  Anything else (PQ, SQ, HNSW, ...) is outside
+    this build (out of scope) and raises ValueError at construction time."""
+    key = key.strip()
+    if key == "Flat":
+        return GpuIndexFlat(d, metric, **kwargs)
+    m = _IVF_FLAT.match(key)
+    if m:
+        return GpuIndexIVFFlat(d, int(m.group(1)), metric, **kwargs)
+    if key == "LSH":
+        return GpuIndexLSH(d, kwargs.pop("nbits", 256), **kwargs)
+    raise ValueError(f"index key '{key}' is not supported by the CUDA build (supported: 'Flat', 'IVF<n>,Flat', 'LSH')")

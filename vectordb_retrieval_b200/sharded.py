@@ -60,11 +60,12 @@ def allgather_topk(dist_local: torch.Tensor, idx_local: torch.Tensor, group=None
     """[nq, k] per rank -> [world, nq, k] on every rank, rank order == ascending id ranges."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    d_all = torch.empty((world,) + tuple(dist_local.shape), dtype=dist_local.dtype, device=dist_local.device)
-    i_all = torch.empty((world,) + tuple(idx_local.shape), dtype=idx_local.dtype, device=idx_local.device)
+    nq, k = dist_local.shape
+    d_all = torch.empty((world * nq, k), dtype=dist_local.dtype, device=dist_local.device)   # rank-major concatenation
+    i_all = torch.empty((world * nq, k), dtype=idx_local.dtype, device=idx_local.device)
     dist.all_gather_into_tensor(d_all, dist_local.contiguous(), group=group)
     dist.all_gather_into_tensor(i_all, idx_local.contiguous(), group=group)
-    return d_all, i_all
+    return d_all.view(world, nq, k), i_all.view(world, nq, k)
 
 
 class ShardedTopK:
