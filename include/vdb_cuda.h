@@ -110,9 +110,13 @@ int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, in
 
 /* Bring-up knob for kernel timing experiments (results are WRONG for mode != 0): 2 = filter
  * but never append a candidate, 3 = do not read the accumulators at all (contraction pipeline
- * only), 5 = start from the bounds the previous call left in the workspace (perfect warm start),
- * 6 = empty a full pool instead of compacting it.  Returns the previous mode. */
+ * only), 5 = start from the bounds the previous call left in the workspace (perfect warm start).
+ * Returns the previous mode. */
 int vdb_set_debug_mode(int mode);
+/* mode 8 (and 9 = 8 with kept bounds): the tcgen05 scan also accumulates epilogue counters; this
+ * reads and clears them: [0] epilogue-warp cycles, [1] of which waiting for an accumulator, [2] for
+ * norms, [3] appended candidates, [4] compactions (per lane), [5] compaction cycles, [6] warps. */
+int vdb_debug_read_prof(uint64_t* out8);
 
 /* Measurement hook for bench.py's roofline leg: while enabled, every vdb_flat_topk call brackets
  * its scan kernel with a pair of CUDA events on the launching stream (up to 512 calls).

@@ -38,6 +38,19 @@ for _ in range(reps):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
+if dbg >= 8:
+    import ctypes
+    buf = (ctypes.c_uint64 * 8)()
+    _lib.load().vdb_debug_read_prof(buf)
+    _ = shard.search(q.clone(), k, 0, 3.4e38, code)
+    torch.cuda.synchronize()
+    _lib.load().vdb_debug_read_prof(buf)
+    tot, wait, nrm, app, ncomp, ccyc, warps, hits = [int(buf[i]) for i in range(8)]
+    print(f"  hit chunks/warp {hits / max(warps, 1):,.0f}, cycles in hit path {100 * nrm / max(tot, 1):.1f}% = {nrm / max(hits, 1):,.0f} cyc per hit chunk; "
+          f"generation 0: {ncomp / max(warps, 1):,.0f} hit chunks/warp, {100 * ccyc / max(tot, 1):.1f}% of cycles, {ccyc / max(ncomp, 1):,.0f} cyc each")
+    print(f"  prof: epilogue warps {warps}, cycles/warp {tot / max(warps, 1):,.0f}, waiting for MMA {100 * wait / max(tot, 1):.1f}%, "
+          f"for norms {100 * nrm / max(tot, 1):.1f}%, compaction {100 * ccyc / max(tot, 1):.1f}% ({ncomp:,} lane-compactions, "
+          f"{ccyc / max(ncomp, 1) * 1.0:,.0f} cyc each incl. peers), appends {app:,} ({app / nq:,.0f} per query)", flush=True)
 ms = float(np.median(ts))
 flops = 2.0 * nq * n * d
 print(f"[{impl} dbg={dbg}] n={n} d={d} nq={nq} k={k} {metric}: median {ms:.3f} ms (min {min(ts):.3f})  "

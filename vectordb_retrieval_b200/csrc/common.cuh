@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <string.h>
 #include <math_constants.h>
 
 #include "../../include/vdb_cuda.h"
@@ -41,7 +43,7 @@ __host__ __device__ __forceinline__ uint32_t f2ord(float f) {
 #else
   uint32_t u; memcpy(&u, &f, 4);
 #endif
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return u ^ (static_cast<uint32_t>(static_cast<int32_t>(u) >> 31) | 0x80000000u);   // negative: ~u, else u | sign
 }
 __host__ __device__ __forceinline__ float ord2f(uint32_t o) {
   uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
@@ -227,6 +229,22 @@ __device__ __noinline__ void warp_sort_noinline(uint64_t* v, int lane) {
   warp_sort<E>(w, lane);
 #pragma unroll
   for (int e = 0; e < E; ++e) v[e] = w[e];
+}
+
+// Spin until *p >= target (a counter another CTA of this co-resident persistent grid increments
+// with a release pattern: data, __threadfence, atomicAdd).  Bounded: a protocol bug traps.
+__device__ __forceinline__ void wait_counter(const int* p, int target) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) return;
+    if (clock64() - t0 > 8000000000ll) {
+      printf("vdb: hand-over wait timed out (block %d, have %d, want %d)\n", blockIdx.x, v, target);
+      __trap();
+    }
+    __nanosleep(100);
+  }
 }
 
 __device__ __forceinline__ float ld_volatile_thr(const uint32_t* p) {

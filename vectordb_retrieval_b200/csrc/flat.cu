@@ -17,8 +17,10 @@ struct FlatPlan {
   int n_tiles;
   int tile_rows;
   int n_chunks;
+  int n_pools;         // pools per query
   int tiles_per_chunk;
   int slots;
+  int clusters;        // tcgen05: persistent clusters launched
 };
 
 static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves) {
@@ -36,11 +38,11 @@ static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves) {
   return best;
 }
 
-static int max_chunks(int64_t nq, int sm) {
-  // upper bound of pick_chunks over every implementation (tile count unbounded)
+static int max_pools(int64_t nq, int sm) {
+  // upper bound of the pools per query over every implementation, independent of the base size
   const int qt128 = static_cast<int>((nq + 127) / 128), qt64 = static_cast<int>((nq + 63) / 64);
-  int a = std::max(1, (sm * 8 + qt128 - 1) / qt128);          // 1-CTA tcgen05 (slots = sm)
-  int b = std::max(1, (2 * sm * 8 + qt64 - 1) / qt64);        // SIMT (slots = 2*sm)
+  const int a = (sm / qt128 + 3) * tc::kEpilogueGroups;              // tcgen05: clusters sharing one query tile
+  const int b = std::max(1, (2 * sm * 8 + qt64 - 1) / qt64);         // SIMT chunks (slots = 2*sm)
   return std::min(std::max(a, b), 2 * sm) + 2;
 }
 
@@ -58,6 +60,13 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
   const int s = pick_chunks(p.n_qtiles, p.n_tiles, p.slots, 8);
   p.tiles_per_chunk = (p.n_tiles + s - 1) / s;
   p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.n_pools = p.n_chunks;
+  if (p.cta_group != 0) {
+    // chunks c and c + L of a query tile are >= one wave apart when L * n_qtiles >= clusters: they
+    // share a pool (lineage), see flat_tc.cuh
+    p.clusters = std::max(1, std::min(p.slots, p.n_qtiles * p.n_chunks));
+    p.n_pools = std::min(p.n_chunks, (p.clusters + p.n_qtiles - 1) / p.n_qtiles);
+  }
   return p;
 }
 
@@ -72,10 +81,12 @@ static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
 static bool g_ev_made = false;
 
 // --------------------------------------------------------------------------------------------
-__global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int keep_thr) {
+__global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int* handover,
+                                 int64_t n_hand, int keep_thr) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < nq_pad && !keep_thr) thr[i] = f2ord(CUDART_INF_F);
   if (i < n_cnt) pool_cnt[i] = 0;
+  if (i < n_hand) handover[i] = 0;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -101,7 +112,7 @@ flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ 
   const int64_t q = q_row0 + tid;              // epilogue role: threads 0..63 own one query each
   const bool epi = tid < 64;
   const bool live = epi && q < P.nq;
-  uint64_t* pool = epi ? P.pools + (q * P.n_chunks + chunk) * CAP : nullptr;
+  uint64_t* pool = epi ? P.pools + (q * P.n_pools + chunk) * CAP : nullptr;
   uint32_t* thr_g = epi ? P.thr + q : nullptr;
   int cnt = 0;
   float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
@@ -149,7 +160,7 @@ flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ 
     }
     __syncthreads();
   }
-  if (epi) P.pool_cnt[q * P.n_chunks + chunk] = cnt;
+  if (epi) P.pool_cnt[q * P.n_pools + chunk] = cnt;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -198,34 +209,49 @@ flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __
   }
   if (staged > 0) flush();
 
-  // exact re-scoring, one candidate at a time, coalesced over the row
+  // exact re-scoring: the warp walks the kept candidates four at a time (four independent row
+  // gathers in flight), each row read coalesced over the lanes; fp32 inputs, fp64 accumulation
   const float* qh = q_hi + q * kpad;
   const float* ql = q_lo + q * kpad;
   uint64_t exact[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     exact[e] = kEmpty;
-    for (int src = 0; src < 32; ++src) {
-      const uint64_t cand = __shfl_sync(0xffffffffu, best[e], src);
-      if (cand == kEmpty) break;               // sorted: nothing valid after the first empty slot
-      const uint32_t row = packed_row(cand);
-      const float* xh = b_hi + static_cast<int64_t>(row) * kpad;
-      const float* xl = b_lo + static_cast<int64_t>(row) * kpad;
-      double acc = 0.0;
+    for (int src0 = 0; src0 < 32; src0 += 4) {
+      uint64_t cand[4];
+      const float* xh[4];
+      const float* xl[4];
+      double acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cand[u] = __shfl_sync(0xffffffffu, best[e], src0 + u);
+        const int64_t row = cand[u] == kEmpty ? 0 : static_cast<int64_t>(packed_row(cand[u]));
+        xh[u] = b_hi + row * kpad;
+        xl[u] = b_lo + row * kpad;
+        acc[u] = 0.0;
+      }
+      if (cand[0] == kEmpty) break;              // sorted: nothing valid after the first empty slot
       for (int j = lane; j < kpad; j += 32) {
-        const float xb = xh[j] + xl[j];
         const float xq = -0.5f * (qh[j] + ql[j]);   // operands hold -2q (exact scaling)
-        if (metric == VDB_METRIC_L2) {
-          const float df = xb - xq;
-          acc += static_cast<double>(df) * static_cast<double>(df);
-        } else {
-          acc += static_cast<double>(xq) * static_cast<double>(xb);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float xb = __ldg(xh[u] + j) + __ldg(xl[u] + j);
+          if (metric == VDB_METRIC_L2) {
+            const float df = xb - xq;
+            acc[u] += static_cast<double>(df) * static_cast<double>(df);
+          } else {
+            acc[u] += static_cast<double>(xq) * static_cast<double>(xb);
+          }
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const float key = metric == VDB_METRIC_L2 ? static_cast<float>(acc) : -static_cast<float>(acc);
-      if (lane == src) exact[e] = pack_key(key, row);
+      for (int u = 0; u < 4; ++u) {
+        double a = acc[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const float key = metric == VDB_METRIC_L2 ? static_cast<float>(a) : -static_cast<float>(a);
+        if (lane == src0 + u && cand[u] != kEmpty) exact[e] = pack_key(key, packed_row(cand[u]));
+      }
     }
   }
   warp_sort_noinline<E>(exact, lane);
@@ -328,7 +354,7 @@ static int make_operand_map(CUtensorMap* map, const float* ptr, int64_t rows, in
 
 template <int CG, bool ARES, int KP, bool DENSE>
 static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mbh, const CUtensorMap& mbl,
-                     const FlatScanParams& P, int sm, cudaStream_t stream) {
+                     const FlatScanParams& P, int clusters, cudaStream_t stream) {
   auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE>;
   constexpr int smem = tc::smem_bytes<ARES>();
   static bool configured[64] = {};
@@ -338,8 +364,6 @@ static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUten
     VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = true;
   }
-  const int n_items = P.n_qtiles * P.n_chunks;
-  const int clusters = std::max(1, std::min(sm / CG, n_items));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(tc::kThreads);
@@ -374,18 +398,18 @@ static int run_scan(int impl, const float* hi, const float* lo, int64_t n_pad, i
   if constexpr (KP == 32) {   // the dense-key test hook exists for the smallest pool size only
     if (P.dense != nullptr) {
       if (plan.cta_group == 2)
-        return ares ? launch_tc<2, true, KP, true>(mqh, mql, mbh, mbl, P, sm, stream)
-                    : launch_tc<2, false, KP, true>(mqh, mql, mbh, mbl, P, sm, stream);
-      return ares ? launch_tc<1, true, KP, true>(mqh, mql, mbh, mbl, P, sm, stream)
-                  : launch_tc<1, false, KP, true>(mqh, mql, mbh, mbl, P, sm, stream);
+        return ares ? launch_tc<2, true, KP, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                    : launch_tc<2, false, KP, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+      return ares ? launch_tc<1, true, KP, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                  : launch_tc<1, false, KP, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
     }
   }
   if (plan.cta_group == 2) {
-    return ares ? launch_tc<2, true, KP, false>(mqh, mql, mbh, mbl, P, sm, stream)
-                : launch_tc<2, false, KP, false>(mqh, mql, mbh, mbl, P, sm, stream);
+    return ares ? launch_tc<2, true, KP, false>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                : launch_tc<2, false, KP, false>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
   }
-  return ares ? launch_tc<1, true, KP, false>(mqh, mql, mbh, mbl, P, sm, stream)
-              : launch_tc<1, false, KP, false>(mqh, mql, mbh, mbl, P, sm, stream);
+  return ares ? launch_tc<1, true, KP, false>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+              : launch_tc<1, false, KP, false>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
 }
 
 template <int KP>
@@ -400,20 +424,23 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   const FlatPlan plan = make_plan(impl, nq, n_pad, sm);
   constexpr int CAP = 2 * KP;
   const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
-  const size_t off_pool = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_chunks * 4);
-  const size_t need = off_pool + static_cast<size_t>(nq_pad) * plan.n_chunks * CAP * 8;
+  const size_t off_hand = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_pools * 4);
+  const size_t off_pool = off_hand + align256(static_cast<size_t>(plan.n_qtiles + 1) * plan.n_pools * 4);
+  const size_t need = off_pool + static_cast<size_t>(nq_pad) * plan.n_pools * CAP * 8;
   VDB_REQUIRE(ws != nullptr && ws_bytes >= need, "vdb_flat_topk: workspace too small (%zu < %zu)", ws_bytes, need);
   uint8_t* w = static_cast<uint8_t*>(ws);
   FlatScanParams P{};
   P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
-  P.n_chunks = plan.n_chunks; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.n_chunks = plan.n_chunks; P.n_pools = plan.n_pools; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.handover = reinterpret_cast<int*>(w + off_hand);
   P.thr = reinterpret_cast<uint32_t*>(w);
   P.pool_cnt = reinterpret_cast<int*>(w + off_cnt);
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
   P.dense = dense; P.dense_ld = n_pad; P.dbg = g_debug_mode;
-  const int64_t n_cnt = nq_pad * plan.n_chunks;
-  flat_init_kernel<<<static_cast<unsigned>((n_cnt + 255) / 256), 256, 0, stream>>>(P.thr, nq_pad, P.pool_cnt, n_cnt,
-                                                                                      g_debug_mode == 5);
+  const int64_t n_cnt = nq_pad * plan.n_pools;
+  const int64_t n_hand = static_cast<int64_t>(plan.n_qtiles + 1) * plan.n_pools;
+  flat_init_kernel<<<static_cast<unsigned>((std::max(n_cnt, n_hand) + 255) / 256), 256, 0, stream>>>(
+      P.thr, nq_pad, P.pool_cnt, n_cnt, P.handover, n_hand, g_debug_mode == 5 || g_debug_mode == 9);
   VDB_CHECK_CUDA(cudaGetLastError());
   const bool timed = g_timing_on && g_timing_n < kTimingSlots;
   if (timed) VDB_CHECK_CUDA(cudaEventRecord(g_ev0[g_timing_n], stream));
@@ -423,7 +450,7 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   count_launches(2 + (out_d != nullptr ? 1 : 0));
   if (out_d != nullptr) {
     flat_finalize_kernel<KP><<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
-        metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, plan.n_chunks, P.pools, P.pool_cnt, k, flags, pad_value,
+        metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, plan.n_pools, P.pools, P.pool_cnt, k, flags, pad_value,
         out_d, out_i);
     VDB_CHECK_CUDA(cudaGetLastError());
   }
@@ -440,6 +467,15 @@ int vdb_set_debug_mode(int mode) {
   const int old = g_debug_mode;
   g_debug_mode = mode;
   return old;
+}
+
+int vdb_debug_read_prof(uint64_t* out8) {
+  unsigned long long h[8] = {};
+  VDB_CHECK_CUDA(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  unsigned long long z[8] = {};
+  VDB_CHECK_CUDA(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+  return 0;
 }
 
 int vdb_flat_timing_enable(int on) {
@@ -472,9 +508,9 @@ size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   const int kp = keep_for_k(k);
   if (kp == 0 || nq <= 0) return 0;
   const int64_t nq_pad = vdb_flat_nqpad(nq);
-  const int s = max_chunks(nq, sm);
+  const int s = max_pools(nq, sm);
   return align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
-         static_cast<size_t>(nq_pad) * s * 2 * kp * 8 + 256;
+         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * 2 * kp * 8 + 256;
 }
 
 int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,

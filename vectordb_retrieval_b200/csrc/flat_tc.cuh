@@ -5,15 +5,19 @@
 // Replaces the arithmetic of faiss.IndexFlat.search (reference src/algorithms/exact_search.py:78)
 // and LinearSearcher.batch_search (reference src/algorithms/modular.py:336-387).
 //
-// One work item = (query tile, base chunk).  Per CTA: 128 queries = 128 TMEM lanes, so each
-// epilogue thread owns one query and sees that query's keys as a register stream.
+// One work item = (query tile, base chunk), handed out chunk-major to a persistent grid (one cluster
+// per SM pair): the clusters of one wave read the same base tiles at about the same time, so the
+// base streams from HBM once per wave and is served from L2 otherwise.  Per CTA: 128 queries = 128
+// TMEM lanes, so each epilogue thread owns one query and sees that query's keys as a register
+// stream.  Candidate pools are per (query, lineage), see the epilogue.
 //   warp 0      TMA producer  : base tiles (hi, lo) -> 128B-swizzled smem ring
 //   warp 1      MMA issuer    : per 32-wide k-block  hi*hi + hi*lo + lo*hi  (kind::tf32, fp32 acc in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue      : tcgen05.ld 32 columns, key = acc + |x|^2 (queries are pre-scaled by
+//   warps 4..7  epilogue      : (TMEM lane quarter = warp % 4)
+//                               tcgen05.ld 32 columns, key = acc + |x|^2 (queries are pre-scaled by
 //                               -2, the tile's norms are bulk-copied to smem by the producer),
 //                               compare against the query's bound, append the rare survivors to
-//                               the query's pool
+//                               the (query, chunk, group) pool
 // kCtaGroup == 2: two CTAs of a cluster form one 256 x 256 UMMA (cta_group::2); each loads half
 // of every base tile, which halves L2->smem traffic per SM.
 #pragma once
@@ -30,23 +34,31 @@ struct FlatScanParams {
   int n_tiles;          // base tiles of TILE_N rows
   int tiles_per_chunk;  // base tiles per work item
   int n_chunks;         // S
+  int n_pools;          // candidate pools per query (tcgen05: lineages L, SIMT: S)
   int n_qtiles;         // query tiles of 128*kCtaGroup rows
+  int* handover;        // tcgen05 kernel: [n_qtiles][n_pools] hand-over counters between the chunks of a lineage
   int kb;               // k-blocks of 32 (kpad / 32)
-  uint64_t* pools;      // [nq_pad][S][2*KP]
-  int* pool_cnt;        // [nq_pad][S]
+  uint64_t* pools;      // [nq_pad][n_pools][2*KP]
+  int* pool_cnt;        // [nq_pad][n_pools]
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
   float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
   int64_t dense_ld;
-  int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 6 drop full pools instead of compacting
+  int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
 
+// bring-up counters (vdb_debug_read_prof): epilogue-warp cycles total / waiting for an accumulator /
+// waiting for norms, appended candidates, compaction calls, compaction cycles
+__device__ unsigned long long g_prof[8];
+
 namespace tc {
-constexpr int kThreads = 256;
+constexpr int kEpilogueGroups = 1;                   // groups of four epilogue warps (tiles alternate between groups)
+constexpr int kThreads = 128 + 128 * kEpilogueGroups;
 constexpr int kStages = 3;
 constexpr int kBlockRows = 128;                      // rows per operand block (A or B half)
 constexpr int kBlockBytes = kBlockRows * 128;        // 16 KB: 128 rows x 32 fp32, SWIZZLE_128B
 constexpr int kMaxResidentKb = 4;                    // query tile stays in smem when kpad <= 128
 constexpr int kNormRingBytes = 2 * 256 * 4;        // |x|^2 of two tiles (<= 256 rows each)
+constexpr int kKeyStageBytes = 0;
 constexpr int kBarrierBytes = 256;
 
 template <bool kAResident>
@@ -54,7 +66,7 @@ constexpr int smem_bytes() {
   // resident: A_hi/A_lo [4] + ring of {B_hi, B_lo};  streamed: ring of {A_hi, A_lo, B_hi, B_lo}
   return (kAResident ? 2 * kMaxResidentKb * kBlockBytes + kStages * 2 * kBlockBytes
                      : kStages * 4 * kBlockBytes) +
-         kNormRingBytes + kBarrierBytes;   // dynamic smem must start 1024-byte aligned (checked)
+         kNormRingBytes + kKeyStageBytes + kBarrierBytes;   // dynamic smem must start 1024-byte aligned (checked)
 }
 }  // namespace tc
 
@@ -82,7 +94,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   uint8_t* ring = smem + (kAResident ? 2 * tc::kMaxResidentKb * tc::kBlockBytes : 0);
   constexpr int kStageBytes = (kAResident ? 2 : 4) * tc::kBlockBytes;
   float* norm_ring = reinterpret_cast<float*>(ring + tc::kStages * kStageBytes);   // [2][UMMA_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(norm_ring) + tc::kNormRingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(norm_ring) + tc::kNormRingBytes + tc::kKeyStageBytes);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA          (leader's are used)
   uint64_t* empty_bar = bars + tc::kStages;        // [kStages]  MMA -> TMA          (every CTA)
   uint64_t* a_full_bar = bars + 2 * tc::kStages;   //            resident A landed   (leader)
@@ -216,29 +228,50 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // 128-bit loads.  Per 32-column chunk a branch-free min tree decides whether any key of this
     // lane beats its bound; only then is the (rare) append code entered.  The chunk loop is a
     // runtime loop over two register buffers so the steady state stays small in the I-cache.
-    const int ew = warp - 4;                       // TMEM lane quarter == warp % 4
+    const int ew = warp & 3;                       // TMEM lane quarter == warp % 4
+    const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;   // epilogue group == accumulator buffer it drains
     constexpr int NCH = UMMA_N / 32;               // 32-column chunks per tile
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     uint32_t va[32], vb[32];
     uint32_t tile_iter = 0;
+    const bool prof = P.dbg >= 8;
+    long long pf_wait = 0, pf_norm = 0, pf_comp = 0, pf_app = 0, pf_ncomp = 0, pf_hits = 0, pf_hitcyc = 0, pf_wait0 = 0;
+    const long long pf_t0 = clock64();
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
       const int t0 = chunk * P.tiles_per_chunk;
       const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
+      // Pool lineage: chunks c, c + L, c + 2L, ... of a query tile run in different waves (L * n_qtiles
+      // >= number of clusters), so they share one pool per query: the successor waits for the
+      // predecessor's hand-over flag and continues with its count, entries and bound.  A query's
+      // bound therefore keeps tightening over ~n / L rows instead of restarting with every chunk.
+      const int slot = chunk % P.n_pools, gen = chunk / P.n_pools;
       const int64_t q = static_cast<int64_t>(qt * kCtaGroup + cta_rank) * 128 + ew * 32 + lane;
       const bool live = q < P.nq;
-      uint64_t* pool = P.pools + (q * P.n_chunks + chunk) * CAP;
+      const int64_t pool_id = q * P.n_pools + slot;
+      uint64_t* pool = P.pools + pool_id * CAP;
       uint32_t* thr_g = P.thr + q;
+      int* handover = P.handover + qt * P.n_pools + slot;   // completed (warp, item) pairs of this lineage
       int cnt = 0;
+      if (gen > 0) {
+        if (lane == 0) wait_counter(handover, gen * 4 * kCtaGroup);
+        __syncwarp();
+        cnt = __ldcg(P.pool_cnt + pool_id);
+      }
       float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
+        if (tc::kEpilogueGroups > 1 && buf != grp) continue;   // the other group's tile
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
         const float thr_seen = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
         const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;
         const float* nb = norm_ring + buf * UMMA_N;
+        long long pf_a = 0, pf_b = 0;
+        if (prof) pf_a = clock64();
         mbar_wait(norm_full_bar + buf, ph);
+        if (prof) pf_b = clock64();
         mbar_wait(tmem_full_bar + buf, ph);
+        if (prof) { pf_wait += clock64() - pf_b; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + buf * UMMA_N;
         auto release_tmem = [&]() {                // every column of this accumulator is in registers
@@ -277,17 +310,28 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
               for (int i = 0; i < 32; ++i) P.dense[q * P.dense_ld + rbase + i] = __uint_as_float(v[i]);
             }
           }
-          if (m < thr && P.dbg != 2) {           // some key of this lane beats its bound (rare)
+          // Append path: every branch is decided by a warp vote and the per-key test only predicates
+          // the store.  Measured on this one-warp-per-scheduler role (cycles per chunk with a hit):
+          // divergent per-key branches ~760, per-group votes (this code) ~670 with tight bounds,
+          // straight-line 32 predicated stores ~1550, smem transpose + ballot per hitting lane ~1100.
+          if (__any_sync(0xffffffffu, m < thr) && P.dbg != 2) {
+            long long th0 = 0;
+            if (prof) { th0 = clock64(); pf_hits += 1; }
+            pool_maintain<KP>(thr, cnt, pool, lane, thr_g);       // room for up to 32 appends per lane
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (gm[g] < thr) {
+              if (__any_sync(0xffffffffu, gm[g] < thr)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float key = __uint_as_float(v[g * 4 + u]);
-                  if (key < thr) { pool[cnt] = pack_key(key, rbase + g * 4 + u); ++cnt; }
+                  const uint64_t packed = pack_key(key, rbase + g * 4 + u);
+                  const bool hit = key < thr;
+                  if (hit) pool[cnt] = packed;
+                  cnt += hit ? 1 : 0;
                 }
               }
             }
+            if (prof) { const long long dt = clock64() - th0; pf_hitcyc += dt; if (gen == 0) { pf_norm += dt; pf_wait0 += 1; } }
           }
         };
 
@@ -296,19 +340,33 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           // chunk c is in flight in va: wait, start chunk c+1 into vb, filter va under that latency
           tmem_ld_wait();
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          if (P.dbg == 6) { if (cnt > CAP - 32) cnt = 0; } else pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
-          consume(va, c);
+          { const int before = cnt; consume(va, c); pf_app += max(cnt - before, 0); }
           tmem_ld_wait();
           if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, va);
           else release_tmem();
-          if (P.dbg == 6) { if (cnt > CAP - 32) cnt = 0; } else pool_maintain<KP>(thr, cnt, pool, lane, thr_g);
-          consume(vb, c + 1);
+          { const int before = cnt; consume(vb, c + 1); pf_app += max(cnt - before, 0); }
         }
         __syncwarp();                              // all lanes are done with this tile's norms
         if (lane == 0) mbar_arrive(norm_empty_bar + buf);
         thr = fminf(thr, thr_seen);
       }
-      P.pool_cnt[q * P.n_chunks + chunk] = cnt;
+      __stcg(P.pool_cnt + pool_id, cnt);
+      __threadfence();                             // pool entries + count before the hand-over flag
+      __syncwarp();
+      if (lane == 0) atomicAdd(handover, 1);
+    }
+    if (prof) {
+      if (lane == 0) {
+        atomicAdd(&g_prof[0], static_cast<unsigned long long>(clock64() - pf_t0));
+        atomicAdd(&g_prof[1], static_cast<unsigned long long>(pf_wait));
+        atomicAdd(&g_prof[5], static_cast<unsigned long long>(pf_norm));     // hit-path cycles in generation-0 items
+        atomicAdd(&g_prof[4], static_cast<unsigned long long>(pf_wait0));    // hit chunks in generation-0 items
+        atomicAdd(&g_prof[6], 1ull);
+        atomicAdd(&g_prof[7], static_cast<unsigned long long>(pf_hits));
+        atomicAdd(&g_prof[2], static_cast<unsigned long long>(pf_hitcyc) << 0);
+      }
+      atomicAdd(&g_prof[3], static_cast<unsigned long long>(pf_app));
+      (void)pf_ncomp; (void)pf_comp;
     }
   }
 
