@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries kept under profiles/.
+
+    python scripts/summarize_ncu.py launches gpurun_out/launches_r1.csv  > profiles/launches_r1.md
+    python scripts/summarize_ncu.py kernel   gpurun_out/prof.ncu-rep     > profiles/scan_kernel_r1.md
+The `kernel` mode also writes profiles/scan_kernel_traffic.json (dram bytes per launch), which
+bench.py reports as roofline.traffic."""
+import csv
+import json
+import os
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def short(name: str) -> str:
+    if "vdb::" not in name:
+        return "torch: " + ("randn" if "normal" in name else "copy / fill / elementwise")
+    name = name.replace("void ", "")
+    for cut in ("<", "("):
+        if cut in name:
+            name = name.split(cut)[0]
+    return name.split("::")[-1]
+
+
+def launches(path: str) -> None:
+    rows = list(csv.reader(open(path)))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = rows[start]
+    ix = {h: i for i, h in enumerate(hdr)}
+    agg = OrderedDict()
+    for r in rows[start + 1:]:
+        if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        unit = r[ix["Metric Unit"]]
+        val = float(r[ix["Metric Value"]].replace(",", ""))
+        us = val / 1e3 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1e3
+        agg.setdefault(short(r[ix["Kernel Name"]]), []).append(us)
+    total = sum(sum(v) for v in agg.values())
+    print(f"# Launch list ({os.path.basename(path)})\n")
+    print("`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 3 --warmup 3 "
+          "--no-cpu-baseline`; per-launch times are cold-cache and serialised - compare shares, not absolutes.\n")
+    print("| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"| `{k}` | {len(v)} | {sum(v) / len(v):,.1f} | {sum(v):,.1f} | {100 * sum(v) / total:.1f} % |")
+
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+    "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "smsp__inst_executed.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpc__cycles_elapsed.avg.per_second",
+]
+
+
+def kernel(path: str) -> None:
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# Scan kernel, `ncu --set full --clock-control none` ({os.path.basename(path)})\n")
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print(f"## `{short(d['Kernel Name'])}` grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
+        print("| metric | value | unit |\n|---|---|---|")
+        for h, u in zip(hdr, units):
+            if any(h.endswith(k) or h == k for k in KEYS) or "pipe_tensor" in h and "pct" in h:
+                print(f"| `{h}` | {d[h]} | {u} |")
+        rd = [float(d[h].replace(",", "")) * (1e9 if units[hdr.index(h)] == "Gbyte" else 1e6 if units[hdr.index(h)] == "Mbyte" else 1)
+              for h in hdr if h == "dram__bytes_read.sum"]
+        wr = [float(d[h].replace(",", "")) * (1e9 if units[hdr.index(h)] == "Gbyte" else 1e6 if units[hdr.index(h)] == "Mbyte" else 1)
+              for h in hdr if h == "dram__bytes_write.sum"]
+        if rd and wr:
+            with open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json"), "w") as f:
+                json.dump({"kernel": short(d["Kernel Name"]), "dram_bytes_per_launch": rd[0] + wr[0], "source": os.path.basename(path)}, f)
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
