@@ -1,0 +1,77 @@
+"""Multi-GPU parity (needs >= 2 visible GPUs; skipped otherwise): the single-process multi-device
+index and the one-process-per-GPU NCCL path must return exactly what one GPU returns."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus() -> int:
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_multi_device_flat_index_matches_single_gpu(metric):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import vectordb_retrieval_b200.algorithms as A
+    rng = np.random.RandomState(3)
+    base = rng.randn(30011, 48).astype(np.float32)
+    queries = rng.randn(257, 48).astype(np.float32)
+    one = A.get_algorithm_instance("ExactSearch", 48, name="one", metric=metric, device="cuda:0")
+    many = A.get_algorithm_instance("ExactSearch", 48, name="many", metric=metric, devices=list(range(_n_gpus())))
+    one.build_index(base)
+    many.build_index(base)
+    d1, i1 = one.batch_search(queries, 50)
+    d2, i2 = many.batch_search(queries, 50)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1, d2)
+    ref = oracle.faiss_flat_search(base, queries, 50, metric)
+    res = oracle.compare_topk(ref[0], ref[1], d2, i2, rtol=1e-5, atol=0.0 if metric == "l2" else 1e-4)
+    assert res["ok"], res
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+rank = int(os.environ["RANK"]); dev = torch.device("cuda", int(os.environ["LOCAL_RANK"])); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+import vectordb_retrieval_b200.algorithms as A
+rng = np.random.RandomState(3)
+base = rng.randn(30011, 48).astype(np.float32); queries = rng.randn(257, 48).astype(np.float32)
+algo = A.get_algorithm_instance("ExactSearch", 48, name="dist", metric="l2", device=dev)
+algo.build_index(base)                       # rows sharded over the ranks
+d, i = algo.batch_search(queries, 50)
+np.save(os.path.join({out!r}, f"d{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i{{rank}}.npy"), i)
+dist.destroy_process_group()
+"""
+
+
+def test_distributed_flat_index_nccl(tmp_path):
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, out=str(tmp_path)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                    "127.0.0.1", "--master-port", str(port), str(script)], check=True, timeout=600)
+    rng = np.random.RandomState(3)
+    base = rng.randn(30011, 48).astype(np.float32)
+    queries = rng.randn(257, 48).astype(np.float32)
+    ref = oracle.faiss_flat_search(base, queries, 50, "l2")
+    for r in range(n):
+        res = oracle.compare_topk(ref[0], ref[1], np.load(tmp_path / f"d{r}.npy"), np.load(tmp_path / f"i{r}.npy"), rtol=1e-5)
+        assert res["ok"], res
+    np.testing.assert_array_equal(np.load(tmp_path / "i0.npy"), np.load(tmp_path / f"i{n - 1}.npy"))

@@ -302,35 +302,45 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             v[g * 4 + 2] = __float_as_uint(k2); v[g * 4 + 3] = __float_as_uint(k3);
             gm[g] = fminf(fminf(k0, k1), fminf(k2, k3));
           }
-          const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])),
-                                fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
           if (kDense) {
             if (live) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) P.dense[q * P.dense_ld + rbase + i] = __uint_as_float(v[i]);
             }
           }
-          // Append path: every branch is decided by a warp vote and the per-key test only predicates
-          // the store.  Measured on this one-warp-per-scheduler role (cycles per chunk with a hit):
-          // divergent per-key branches ~760, per-group votes (this code) ~670 with tight bounds,
-          // straight-line 32 predicated stores ~1550, smem transpose + ballot per hitting lane ~1100.
-          if (__any_sync(0xffffffffu, m < thr) && P.dbg != 2) {
+          // Append path.  Every branch is warp-uniform: the lanes OR their 8-bit masks of 4-column
+          // groups that beat the bound (one redux), the warp visits only those groups, and the
+          // per-key test merely predicates the store.  This role runs one warp per scheduler, so
+          // branch / scoreboard latency is exposed; measured cycles per chunk with a hit: divergent
+          // per-key branches ~760, one vote per group ~670, 32 straight-line predicated stores
+          // ~1550, smem transpose + ballot per hitting lane ~1100.
+          unsigned gmask = 0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) gmask |= gm[g] < thr ? (1u << g) : 0u;
+          unsigned todo = __reduce_or_sync(0xffffffffu, gmask);
+          if (todo != 0u && P.dbg != 2) {
             long long th0 = 0;
             if (prof) { th0 = clock64(); pf_hits += 1; }
             pool_maintain<KP>(thr, cnt, pool, lane, thr_g);       // room for up to 32 appends per lane
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (__any_sync(0xffffffffu, gm[g] < thr)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float key = __uint_as_float(v[g * 4 + u]);
-                  const uint64_t packed = pack_key(key, rbase + g * 4 + u);
-                  const bool hit = key < thr;
-                  if (hit) pool[cnt] = packed;
-                  cnt += hit ? 1 : 0;
-                }
+#define VDB_APPEND_GROUP(G)                                                          \
+  case G: {                                                                          \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                  \
+      const float key = __uint_as_float(v[G * 4 + u]);                               \
+      const uint64_t packed = pack_key(key, rbase + G * 4 + u);                      \
+      const bool hit = key < thr;                                                    \
+      if (hit) pool[cnt] = packed;                                                   \
+      cnt += hit ? 1 : 0;                                                            \
+    }                                                                                \
+  } break;
+            while (todo != 0u) {
+              const int g = __ffs(todo) - 1;
+              todo &= todo - 1;
+              switch (g) {
+                VDB_APPEND_GROUP(0) VDB_APPEND_GROUP(1) VDB_APPEND_GROUP(2) VDB_APPEND_GROUP(3)
+                VDB_APPEND_GROUP(4) VDB_APPEND_GROUP(5) VDB_APPEND_GROUP(6) VDB_APPEND_GROUP(7)
               }
             }
+#undef VDB_APPEND_GROUP
             if (prof) { const long long dt = clock64() - th0; pf_hitcyc += dt; if (gen == 0) { pf_norm += dt; pf_wait0 += 1; } }
           }
         };
