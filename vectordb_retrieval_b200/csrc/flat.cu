@@ -426,13 +426,15 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
   const size_t off_hand = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_pools * 4);
   const size_t off_pool = off_hand + align256(static_cast<size_t>(plan.n_qtiles + 1) * plan.n_pools * 4);
-  const size_t need = off_pool + static_cast<size_t>(nq_pad) * plan.n_pools * CAP * 8;
+  const size_t off_trash = off_pool + static_cast<size_t>(nq_pad) * plan.n_pools * CAP * 8;
+  const size_t need = off_trash + static_cast<size_t>(nq_pad) * 8;
   VDB_REQUIRE(ws != nullptr && ws_bytes >= need, "vdb_flat_topk: workspace too small (%zu < %zu)", ws_bytes, need);
   uint8_t* w = static_cast<uint8_t*>(ws);
   FlatScanParams P{};
   P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
   P.n_chunks = plan.n_chunks; P.n_pools = plan.n_pools; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
   P.handover = reinterpret_cast<int*>(w + off_hand);
+  P.trash = reinterpret_cast<uint64_t*>(w + off_trash);
   P.thr = reinterpret_cast<uint32_t*>(w);
   P.pool_cnt = reinterpret_cast<int*>(w + off_cnt);
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
@@ -510,7 +512,8 @@ size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   const int64_t nq_pad = vdb_flat_nqpad(nq);
   const int s = max_pools(nq, sm);
   return align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
-         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * 2 * kp * 8 + 256;
+         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * 2 * kp * 8 +
+         static_cast<size_t>(nq_pad) * 8 + 256;
 }
 
 int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,

@@ -36,6 +36,7 @@ struct FlatScanParams {
   int n_chunks;         // S
   int n_pools;          // candidate pools per query (tcgen05: lineages L, SIMT: S)
   int n_qtiles;         // query tiles of 128*kCtaGroup rows
+  uint64_t* trash;      // tcgen05 kernel: [nq_pad] write-only slots for keys that miss the bound
   int* handover;        // tcgen05 kernel: [n_qtiles][n_pools] hand-over counters between the chunks of a lineage
   int kb;               // k-blocks of 32 (kpad / 32)
   uint64_t* pools;      // [nq_pad][n_pools][2*KP]
@@ -308,39 +309,33 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
               for (int i = 0; i < 32; ++i) P.dense[q * P.dense_ld + rbase + i] = __uint_as_float(v[i]);
             }
           }
-          // Append path.  Every branch is warp-uniform: the lanes OR their 8-bit masks of 4-column
-          // groups that beat the bound (one redux), the warp visits only those groups, and the
-          // per-key test merely predicates the store.  This role runs one warp per scheduler, so
-          // branch / scoreboard latency is exposed; measured cycles per chunk with a hit: divergent
-          // per-key branches ~760, one vote per group ~670, 32 straight-line predicated stores
-          // ~1550, smem transpose + ballot per hitting lane ~1100.
+          // Append path.  The lanes OR their 8-bit masks of 4-column groups that beat the bound (one
+          // redux); the warp then tests the bits of that warp-uniform mask and visits only flagged
+          // groups, where the per-key test merely predicates the store.  This role runs one warp per
+          // scheduler, so branch / scoreboard latency is exposed; measured cycles per chunk with a hit:
+          // divergent per-key branches ~760, one vote per group ~670, 32 straight-line predicated
+          // stores ~1550, smem transpose + ballot per hitting lane ~1100, redux + switch loop ~1090.
           unsigned gmask = 0;
 #pragma unroll
           for (int g = 0; g < 8; ++g) gmask |= gm[g] < thr ? (1u << g) : 0u;
-          unsigned todo = __reduce_or_sync(0xffffffffu, gmask);
-          if (todo != 0u && P.dbg != 2) {
+          const unsigned um = __reduce_or_sync(0xffffffffu, gmask);
+          if (um != 0u && P.dbg != 2) {
             long long th0 = 0;
             if (prof) { th0 = clock64(); pf_hits += 1; }
             pool_maintain<KP>(thr, cnt, pool, lane, thr_g);       // room for up to 32 appends per lane
-#define VDB_APPEND_GROUP(G)                                                          \
-  case G: {                                                                          \
-    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                  \
-      const float key = __uint_as_float(v[G * 4 + u]);                               \
-      const uint64_t packed = pack_key(key, rbase + G * 4 + u);                      \
-      const bool hit = key < thr;                                                    \
-      if (hit) pool[cnt] = packed;                                                   \
-      cnt += hit ? 1 : 0;                                                            \
-    }                                                                                \
-  } break;
-            while (todo != 0u) {
-              const int g = __ffs(todo) - 1;
-              todo &= todo - 1;
-              switch (g) {
-                VDB_APPEND_GROUP(0) VDB_APPEND_GROUP(1) VDB_APPEND_GROUP(2) VDB_APPEND_GROUP(3)
-                VDB_APPEND_GROUP(4) VDB_APPEND_GROUP(5) VDB_APPEND_GROUP(6) VDB_APPEND_GROUP(7)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (um & (1u << g)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float key = __uint_as_float(v[g * 4 + u]);
+                  const uint64_t packed = pack_key(key, rbase + g * 4 + u);
+                  const bool hit = key < thr;
+                  if (hit) pool[cnt] = packed;
+                  cnt += hit ? 1 : 0;
+                }
               }
             }
-#undef VDB_APPEND_GROUP
             if (prof) { const long long dt = clock64() - th0; pf_hitcyc += dt; if (gen == 0) { pf_norm += dt; pf_wait0 += 1; } }
           }
         };
