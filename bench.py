@@ -231,16 +231,17 @@ def run_ours(args) -> int:
     def step_device():
         return index.search(q_dev, TOPK)
 
-    # ---- warm-up (also sizes workspaces, creates the NCCL channels)
+    # ---- warm-up (also sizes workspaces, creates the NCCL channels); the clock sampler starts here so
+    # that the 100 ms nvidia-smi period yields enough samples under load
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
         algo.batch_search(q_host_np, TOPK)
     barrier()
 
     # ---- timed: device-resident queries
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.vdb_flat_timing_enable(1)
     launches0 = lib.vdb_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def short(name: str) -> str:
-    if "vdb::" not in name:
+    if "at::" in name or "vectorized_elementwise" in name:
         return "torch: " + ("randn" if "normal" in name else "copy / fill / elementwise")
     name = name.replace("void ", "")
     for cut in ("<", "("):

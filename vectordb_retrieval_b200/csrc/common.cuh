@@ -247,6 +247,13 @@ __device__ __forceinline__ void wait_counter(const int* p, int target) {
   }
 }
 
+// raw (ordered-uint) form: convert with ord2f at the point of use, so that the scoreboard wait
+// for this L2 round trip lands there and not right behind the load
+__device__ __forceinline__ uint32_t ld_volatile_thr_raw(const uint32_t* p) {
+  uint32_t o;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(o) : "l"(p));
+  return o;
+}
 __device__ __forceinline__ float ld_volatile_thr(const uint32_t* p) {
   uint32_t o;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(o) : "l"(p));

@@ -264,7 +264,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
         if (tc::kEpilogueGroups > 1 && buf != grp) continue;   // the other group's tile
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
-        const float thr_seen = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
+        const uint32_t thr_seen = ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
         const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;
         const float* nb = norm_ring + buf * UMMA_N;
         long long pf_a = 0, pf_b = 0;
@@ -353,7 +353,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
         __syncwarp();                              // all lanes are done with this tile's norms
         if (lane == 0) mbar_arrive(norm_empty_bar + buf);
-        thr = fminf(thr, thr_seen);
+        if (live) thr = fminf(thr, ord2f(thr_seen));
       }
       __stcg(P.pool_cnt + pool_id, cnt);
       __threadfence();                             // pool entries + count before the hand-over flag
