@@ -23,13 +23,20 @@ struct FlatPlan {
   int clusters;        // tcgen05: persistent clusters launched
 };
 
-static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves) {
+// Number of base chunks S.  Two constraints: (a) enough (query tile, chunk) items to fill the
+// persistent grid evenly - pick the S with the best wave efficiency; (b) a chunk must fit the L2
+// (`max_tiles`): the clusters of a wave read the same chunk, and only while it is L2-resident does
+// each base tile leave HBM once per wave instead of once per query tile (at 100M x 128 an
+// unbounded chunk of 9 GB let the clusters drift apart and the scan became HBM-bound).
+static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves, int max_tiles) {
   int s_max = std::max(1, (slots * waves + n_qtiles - 1) / n_qtiles);
   s_max = std::min(s_max, std::max(slots, 16));   // few query tiles: one chunk per slot is enough
+  const int s_min = std::min(std::max(1, n_tiles), (n_tiles + max_tiles - 1) / max_tiles);
+  s_max = std::max(s_max, s_min + s_min / 4 + 1);
   s_max = std::min(s_max, std::max(1, n_tiles));
-  int best = 1;
+  int best = s_min;
   double best_eff = -1.0;
-  for (int s = 1; s <= s_max; ++s) {
+  for (int s = s_min; s <= s_max; ++s) {
     const long items = static_cast<long>(n_qtiles) * s;
     const long rounds = (items + slots - 1) / slots;
     const double eff = static_cast<double>(items) / static_cast<double>(rounds * slots);
@@ -46,7 +53,7 @@ static int max_pools(int64_t nq, int sm) {
   return std::min(std::max(a, b), 2 * sm) + 2;
 }
 
-static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
+static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int kpad, int sm) {
   FlatPlan p{};
   if (impl == VDB_IMPL_SIMT) {
     p.cta_group = 0; p.tile_rows = 64; p.slots = 2 * sm;
@@ -57,7 +64,9 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int sm) {
     p.n_qtiles = static_cast<int>((nq + p.tile_rows - 1) / p.tile_rows);
   }
   p.n_tiles = static_cast<int>(n_pad / p.tile_rows);
-  const int s = pick_chunks(p.n_qtiles, p.n_tiles, p.slots, 8);
+  const int64_t tile_bytes = static_cast<int64_t>(p.tile_rows) * kpad * 8;        // hi + lo
+  const int max_tiles = p.cta_group == 0 ? (1 << 30) : static_cast<int>(std::max<int64_t>(8, (48ll << 20) / tile_bytes));
+  const int s = pick_chunks(p.n_qtiles, p.n_tiles, p.slots, 8, max_tiles);
   p.tiles_per_chunk = (p.n_tiles + s - 1) / s;
   p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   p.n_pools = p.n_chunks;
@@ -421,7 +430,7 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   if (vdb_sm_count(&sm)) return 1;
   const int kpad = vdb_flat_kpad(d);
   const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
-  const FlatPlan plan = make_plan(impl, nq, n_pad, sm);
+  const FlatPlan plan = make_plan(impl, nq, n_pad, kpad, sm);
   constexpr int CAP = 2 * KP;
   const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
   const size_t off_hand = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_pools * 4);
