@@ -196,6 +196,7 @@ def run_ours(args) -> int:
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("VDB_NCCL_DEBUG", "WARN")   # stdout carries ONE JSON line, nothing else
         dist.init_process_group("nccl", device_id=dev)
 
     from vectordb_retrieval_b200 import _lib, engine, sharded

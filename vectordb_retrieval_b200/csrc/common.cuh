@@ -65,6 +65,11 @@ __host__ __device__ constexpr int keep_for_k(int k) {
   return k + 8 <= 32 ? 32 : k + 8 <= 128 ? 128 : k + 8 <= 256 ? 256 : k + 8 <= 512 ? 512 : 0;
 }
 
+// Slots of a candidate pool that keeps the best kp: the owner may append until fewer than 32 slots
+// are free, then the pool is cut back to kp.  2*kp leaves kp - 32 appends between two cuts; for
+// kp = 32 that would be none (a cut after every append), so small pools get 4*kp.
+__host__ __device__ constexpr int pool_cap(int kp) { return kp < 64 ? 4 * kp : 2 * kp; }
+
 // ---------------------------------------------------------------------------------------------
 // Bitonic sort of 32*E packed words held by one warp, element i = e*32 + lane, ascending.
 template <int E>
@@ -103,7 +108,7 @@ __device__ __forceinline__ void warp_sort(uint64_t (&v)[E], int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-query candidate pool in global memory (L2 resident): CAP = 2*KP slots.  The owner
+// Per-query candidate pool in global memory (L2 resident): CAP = pool_cap(KP) slots.  The owner
 // thread appends every key that beats its running bound `thr`; when fewer than 32 free slots
 // remain the whole warp selects that pool's best KP (radix select, no sort) and tightens `thr`
 // to the KP-th key - a valid bound because at least KP scanned rows are <= it.  All 32 lanes call.
@@ -145,7 +150,7 @@ __device__ __forceinline__ uint32_t warp_select_kth(const uint32_t (&w)[E], cons
 template <int KP>
 __device__ __noinline__ PoolState pool_compact(unsigned need, float thr, int cnt, uint64_t* pool, int lane,
                                                uint32_t* thr_shared) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   constexpr int E = CAP / 32;
   const unsigned lt_mask = (1u << lane) - 1u;
   while (need) {
@@ -202,7 +207,7 @@ __device__ __noinline__ PoolState pool_compact(unsigned need, float thr, int cnt
 template <int KP>
 __device__ __forceinline__ void pool_maintain(float& thr, int& cnt, uint64_t* pool, int lane,
                                               uint32_t* thr_shared /* this lane's global bound, may be null */) {
-  const unsigned need = __ballot_sync(0xffffffffu, cnt > 2 * KP - 32);
+  const unsigned need = __ballot_sync(0xffffffffu, cnt > pool_cap(KP) - 32);
   if (need) {
     const PoolState st = pool_compact<KP>(need, thr, cnt, pool, lane, thr_shared);
     thr = st.thr;

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256)
 flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ b_lo,
                       const float* __restrict__ q_hi, const float* __restrict__ q_lo, int kpad,
                       const FlatScanParams P) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   __shared__ float Qs[64][33];
   __shared__ float Bs[64][33];
   __shared__ float Ss[64][65];
@@ -182,7 +182,7 @@ flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __
                      int64_t n, int64_t id_offset, const float* __restrict__ q_hi, const float* __restrict__ q_lo,
                      int64_t nq, int n_chunks, const uint64_t* __restrict__ pools, const int* __restrict__ pool_cnt,
                      int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   constexpr int E = KP / 32;
   __shared__ uint64_t stage_all[4][KP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -431,7 +431,7 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   const int kpad = vdb_flat_kpad(d);
   const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
   const FlatPlan plan = make_plan(impl, nq, n_pad, kpad, sm);
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
   const size_t off_hand = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_pools * 4);
   const size_t off_pool = off_hand + align256(static_cast<size_t>(plan.n_qtiles + 1) * plan.n_pools * 4);
@@ -521,7 +521,7 @@ size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   const int64_t nq_pad = vdb_flat_nqpad(nq);
   const int s = max_pools(nq, sm);
   return align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
-         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * 2 * kp * 8 +
+         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * pool_cap(kp) * 8 +
          static_cast<size_t>(nq_pad) * 8 + 256;
 }
 

@@ -39,7 +39,7 @@ struct FlatScanParams {
   uint64_t* trash;      // tcgen05 kernel: [nq_pad] write-only slots for keys that miss the bound
   int* handover;        // tcgen05 kernel: [n_qtiles][n_pools] hand-over counters between the chunks of a lineage
   int kb;               // k-blocks of 32 (kpad / 32)
-  uint64_t* pools;      // [nq_pad][n_pools][2*KP]
+  uint64_t* pools;      // [nq_pad][n_pools][pool_cap(KP)]
   int* pool_cnt;        // [nq_pad][n_pools]
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
   float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
@@ -81,7 +81,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   constexpr int UMMA_M = 128 * kCtaGroup;
   constexpr int UMMA_N = 128 * kCtaGroup;     // base rows per tile (each CTA loads 128 of them)
   constexpr int TMEM_COLS = 2 * UMMA_N;       // double-buffered accumulator
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];

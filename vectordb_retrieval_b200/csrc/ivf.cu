@@ -57,7 +57,7 @@ ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __re
                 const int32_t* __restrict__ blk_off, int nlist, int d4, const int64_t* __restrict__ probes, int nprobe,
                 const float* __restrict__ qmat, int64_t ld_q, int d, int k, int flags, float pad_value, int64_t id_offset,
                 float* __restrict__ out_d, int64_t* __restrict__ out_i, unsigned long long* scanned) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
   int* cnts = reinterpret_cast<int*>(pools + W * CAP);
@@ -109,7 +109,7 @@ static int launch_scan(int metric, const float* vecs, const int32_t* ids, const 
                        float pad_value, int64_t id_offset, float* out_d, int64_t* out_i, int64_t* scanned,
                        cudaStream_t stream) {
   const int d4 = (d + 3) / 4;
-  const size_t smem = static_cast<size_t>(W) * 2 * KP * 8 + W * 4 + static_cast<size_t>(d4) * 16;
+  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>(d4) * 16;
   auto kern = ivf_scan_kernel<KP, W>;
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(

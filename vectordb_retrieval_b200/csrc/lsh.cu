@@ -10,9 +10,13 @@
 //   3. emit    second pass in row order: rows below t* and the first r rows of bin t* are written
 //              at offset[bin] + rank - a stable counting sort, so the output is ordered by
 //              (distance, id) without sorting anything.
-// One warp owns QT queries (codes in registers) and streams the row codes with 128-bit loads, one
-// row per lane; there is no inter-warp communication, hence the row order and the result are
-// deterministic.  Integer / byte work: bound by the popc + compare issue rate and L2 bandwidth.
+// One warp owns QT queries (codes in registers) and streams the row codes of one row segment with
+// 128-bit loads, one row per lane (next 32 rows prefetched); the base is cut into RS segments so
+// that (nq / QT) * RS warps fill the machine, and every (segment, query, bin) keeps its own count,
+// so the output offsets - and with them the row order and the result - stay deterministic.
+// Integer / byte work: bound by the popc + compare issue rate and L2 bandwidth.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vdb {
@@ -55,19 +59,22 @@ __device__ __forceinline__ int hamming(const uint4 (&a)[W4], const uint4 (&b)[W4
 template <int W4>
 constexpr int queries_per_warp() { return W4 <= 2 ? 8 : (W4 == 4 ? 4 : 2); }
 
-// Histogram of the distances <= T[q] over rows [row_begin, row_end).  T == nullptr: every distance.
+// Histogram of the distances <= T[q] over the rows of segment blockIdx.y (rows [row_begin, row_end)
+// cut into gridDim.y segments of seg_len rows) -> hist[seg][q][bin].  T == nullptr: every distance.
 // `only` (nullable): process just the flagged queries.
 template <int W4>
 __global__ void __launch_bounds__(128)
-hamming_count_kernel(const uint4* __restrict__ codes, int64_t row_begin, int64_t row_end, const uint4* __restrict__ qcodes,
-                     int64_t nq, int nbits, const int* __restrict__ T, const uint8_t* __restrict__ only,
-                     int* __restrict__ hist /* [nq][nbits + 1] */) {
+hamming_count_kernel(const uint4* __restrict__ codes, int64_t row_begin, int64_t row_end, int64_t seg_len,
+                     const uint4* __restrict__ qcodes, int64_t nq, int nbits, const int* __restrict__ T,
+                     const uint8_t* __restrict__ only, int* __restrict__ hist /* [segs][nq][nbits + 1] */) {
   constexpr int QT = queries_per_warp<W4>();
   extern __shared__ int smem_i[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bins = nbits + 1;
   const int64_t q0 = (static_cast<int64_t>(blockIdx.x) * 4 + warp) * QT;
   if (q0 >= nq) return;
+  const int64_t r0 = row_begin + static_cast<int64_t>(blockIdx.y) * seg_len;
+  const int64_t r1 = min(row_end, r0 + seg_len);
   int* h = smem_i + warp * QT * bins;
   for (int i = lane; i < QT * bins; i += 32) h[i] = 0;
   uint4 qc[QT][W4];
@@ -84,12 +91,17 @@ hamming_count_kernel(const uint4* __restrict__ codes, int64_t row_begin, int64_t
   }
   if (!any) return;
   __syncwarp();
-  for (int64_t row0 = row_begin; row0 < row_end; row0 += 32) {
+  uint4 nxt[W4];
+#pragma unroll
+  for (int w = 0; w < W4; ++w) nxt[w] = r0 + lane < r1 ? __ldg(codes + (r0 + lane) * W4 + w) : make_uint4(0, 0, 0, 0);
+  for (int64_t row0 = r0; row0 < r1; row0 += 32) {
     const int64_t row = row0 + lane;
-    const bool valid = row < row_end;
+    const bool valid = row < r1;
     uint4 c[W4];
 #pragma unroll
-    for (int w = 0; w < W4; ++w) c[w] = valid ? __ldg(codes + row * W4 + w) : make_uint4(0, 0, 0, 0);
+    for (int w = 0; w < W4; ++w) c[w] = nxt[w];
+#pragma unroll
+    for (int w = 0; w < W4; ++w) nxt[w] = row + 32 < r1 ? __ldg(codes + (row + 32) * W4 + w) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
       const int dist = hamming<W4>(c, qc[qi]);
@@ -97,10 +109,11 @@ hamming_count_kernel(const uint4* __restrict__ codes, int64_t row_begin, int64_t
     }
   }
   __syncwarp();
+  int* out = hist + static_cast<int64_t>(blockIdx.y) * nq * bins;
 #pragma unroll
   for (int qi = 0; qi < QT; ++qi) {
     if (tq[qi] >= 0) {
-      for (int b = lane; b < bins; b += 32) hist[(q0 + qi) * bins + b] = h[qi * bins + b];
+      for (int b = lane; b < bins; b += 32) out[(q0 + qi) * bins + b] = h[qi * bins + b];
     }
   }
 }
@@ -122,45 +135,65 @@ __global__ void hamming_bound_kernel(const int* __restrict__ hist, int64_t nq, i
   T[q] = t;
 }
 
-// hist -> (cut bin, rows to take from it, exclusive prefix written back into hist).  A query whose
-// bound turned out too small (fewer than k rows counted) is flagged for a full recount.
-__global__ void hamming_cut_kernel(int* __restrict__ hist, int64_t nq, int nbits, int k, int* __restrict__ T,
-                                   const uint8_t* __restrict__ only, int* __restrict__ cut, int* __restrict__ take,
-                                   uint8_t* __restrict__ redo) {
+// Per-segment counts -> cut bin t*, and for every segment the rows it takes from bin t* (the first
+// `k - (rows below t*)` rows of that bin in row order) and its output offset per bin (written back
+// over the counts).  A query whose bound turned out too small is flagged for a full recount.
+__global__ void hamming_cut_kernel(int* __restrict__ hist /* [segs][nq][bins] */, int segs, int64_t nq, int nbits, int k,
+                                   int* __restrict__ T, const uint8_t* __restrict__ only, int* __restrict__ cut,
+                                   int* __restrict__ take /* [segs][nq] */, uint8_t* __restrict__ redo) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   if (only != nullptr && only[q] == 0) { if (redo != nullptr) redo[q] = 0; return; }
   const int bins = nbits + 1;
+  const int64_t seg_stride = nq * bins;
   const int bound = T != nullptr ? T[q] : nbits;
   long long cum = 0;
-  int t = -1;
-  for (int b = 0; b <= bound; ++b) {
-    const int c = hist[q * bins + b];
-    hist[q * bins + b] = static_cast<int>(cum);      // exclusive prefix = output offset of bin b
-    if (t < 0 && cum + c >= k) { t = b; take[q] = static_cast<int>(k - cum); }
-    cum += c;
+  int t = -1, need = 0;
+  for (int b = 0; b <= bound && t < 0; ++b) {
+    long long c = 0;
+    for (int s = 0; s < segs; ++s) c += hist[s * seg_stride + q * bins + b];
+    if (cum + c >= k) { t = b; need = static_cast<int>(k - cum); }
+    else cum += c;
   }
   if (t < 0) {
     if (bound < nbits && redo != nullptr) {            // the estimate was too tight: count everything
       redo[q] = 1;
       T[q] = nbits;
       cut[q] = -1;
-      take[q] = 0;
+      for (int s = 0; s < segs; ++s) take[s * nq + q] = 0;
       return;
     }
-    t = nbits + 1;                                     // fewer than k rows exist: take them all
-    take[q] = 0;
+    t = bound;                                         // fewer than k rows exist: take them all
+    need = 1 << 30;
+  }
+  // offsets: bins in ascending order, inside a bin the segments in row order
+  long long run = 0;
+  for (int b = 0; b <= t; ++b) {
+    for (int s = 0; s < segs; ++s) {
+      int* p = hist + s * seg_stride + q * bins + b;
+      const int c = *p;
+      *p = static_cast<int>(min(run, static_cast<long long>(k)));
+      if (b == t) {
+        const int tk = min(need, c);
+        take[s * nq + q] = tk;
+        need -= tk;
+        run += tk;
+      } else {
+        run += c;
+      }
+    }
   }
   cut[q] = t;
   if (redo != nullptr) redo[q] = 0;
 }
 
-// Emission in row order.  offs = hist after the cut kernel (exclusive prefix per bin).
+// Emission in row order within segment blockIdx.y.  offs = hist after the cut kernel.
 template <int W4>
 __global__ void __launch_bounds__(128)
-hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, const uint4* __restrict__ qcodes, int64_t nq, int nbits,
-                    const int* __restrict__ cut, const int* __restrict__ take, const int* __restrict__ offs, int k,
-                    int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, int64_t seg_len, const uint4* __restrict__ qcodes,
+                    int64_t nq, int nbits, const int* __restrict__ cut, const int* __restrict__ take,
+                    const int* __restrict__ offs, int k, int64_t id_offset, float* __restrict__ out_d,
+                    int64_t* __restrict__ out_i) {
   constexpr int QT = queries_per_warp<W4>();
   extern __shared__ int smem_i[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +201,10 @@ hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, const uint4* __r
   const int bins = nbits + 1;
   const int64_t q0 = (static_cast<int64_t>(blockIdx.x) * 4 + warp) * QT;
   if (q0 >= nq) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * seg_len;
+  const int64_t r1 = min(n, r0 + seg_len);
+  const int* seg_offs = offs + static_cast<int64_t>(blockIdx.y) * nq * bins;
+  const int* seg_take = take + static_cast<int64_t>(blockIdx.y) * nq;
   int* cursor = smem_i + warp * QT * bins;
   uint4 qc[QT][W4];
   int cq[QT], rq[QT], seen[QT];
@@ -176,19 +213,24 @@ hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, const uint4* __r
     const int64_t q = q0 + qi;
     const bool live = q < nq;
     cq[qi] = live ? cut[q] : -1;
-    rq[qi] = live ? take[q] : 0;
+    rq[qi] = live ? seg_take[q] : 0;
     seen[qi] = 0;
-    for (int b = lane; b < bins; b += 32) cursor[qi * bins + b] = live ? offs[q * bins + b] : 0;
+    for (int b = lane; b < bins; b += 32) cursor[qi * bins + b] = live ? seg_offs[q * bins + b] : 0;
 #pragma unroll
     for (int w = 0; w < W4; ++w) qc[qi][w] = live ? qcodes[q * W4 + w] : make_uint4(0, 0, 0, 0);
   }
   __syncwarp();
-  for (int64_t row0 = 0; row0 < n; row0 += 32) {
+  uint4 nxt[W4];
+#pragma unroll
+  for (int w = 0; w < W4; ++w) nxt[w] = r0 + lane < r1 ? __ldg(codes + (r0 + lane) * W4 + w) : make_uint4(0, 0, 0, 0);
+  for (int64_t row0 = r0; row0 < r1; row0 += 32) {
     const int64_t row = row0 + lane;
-    const bool valid = row < n;
+    const bool valid = row < r1;
     uint4 c[W4];
 #pragma unroll
-    for (int w = 0; w < W4; ++w) c[w] = valid ? __ldg(codes + row * W4 + w) : make_uint4(0, 0, 0, 0);
+    for (int w = 0; w < W4; ++w) c[w] = nxt[w];
+#pragma unroll
+    for (int w = 0; w < W4; ++w) nxt[w] = row + 32 < r1 ? __ldg(codes + (row + 32) * W4 + w) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
       const int dist = hamming<W4>(c, qc[qi]);
@@ -217,17 +259,27 @@ hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, const uint4* __r
   }
 }
 
+static int hamming_segments(int64_t n, int64_t nq, int qt) {
+  const int64_t warps = (nq + qt - 1) / qt;
+  int64_t segs = (8192 + warps - 1) / warps;                 // aim at ~8k warps in flight
+  segs = std::min<int64_t>(segs, std::max<int64_t>(1, n / 32768));
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(segs, 32)));
+}
+
 template <int W4>
 static int run_hamming(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
                        int64_t id_offset, float* out_d, int64_t* out_i, void* ws, cudaStream_t s) {
   constexpr int QT = queries_per_warp<W4>();
   const int bins = nbits + 1;
+  const int segs = hamming_segments(n, nq, QT);
+  const int64_t seg_len = ((n + segs - 1) / segs + 31) / 32 * 32;
   uint8_t* w = static_cast<uint8_t*>(ws);
-  int* hist = reinterpret_cast<int*>(w);
-  size_t off = (static_cast<size_t>(nq) * bins * 4 + 255) & ~size_t(255);
-  int* T = reinterpret_cast<int*>(w + off);   off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
-  int* cut = reinterpret_cast<int*>(w + off); off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
-  int* take = reinterpret_cast<int*>(w + off); off += (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  int* hist = reinterpret_cast<int*>(w);                     // [segs][nq][bins]
+  size_t off = al(static_cast<size_t>(segs) * nq * bins * 4);
+  int* take = reinterpret_cast<int*>(w + off); off += al(static_cast<size_t>(segs) * nq * 4);
+  int* T = reinterpret_cast<int*>(w + off);    off += al(static_cast<size_t>(nq) * 4);
+  int* cut = reinterpret_cast<int*>(w + off);  off += al(static_cast<size_t>(nq) * 4);
   uint8_t* redo = w + off;
   const uint4* c4 = reinterpret_cast<const uint4*>(codes);
   const uint4* q4 = reinterpret_cast<const uint4*>(qcodes);
@@ -240,22 +292,23 @@ static int run_hamming(const uint32_t* codes, int64_t n, const uint32_t* qcodes,
     VDB_CHECK_CUDA(cudaFuncSetAttribute(count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     VDB_CHECK_CUDA(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
+  const dim3 grid(blocks, segs);
   constexpr int64_t kSample = 32768;
   if (n <= 2 * kSample) {            // small base: one exact count
-    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, nullptr, nullptr, hist);
-    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, nullptr, nullptr, cut, take, nullptr);
+    count<<<grid, 128, smem, s>>>(c4, 0, n, seg_len, q4, nq, nbits, nullptr, nullptr, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, nullptr, nullptr, cut, take, nullptr);
     count_launches(2);
   } else {
-    count<<<blocks, 128, smem, s>>>(c4, 0, kSample, q4, nq, nbits, nullptr, nullptr, hist);
+    count<<<dim3(blocks, 1), 128, smem, s>>>(c4, 0, kSample, kSample, q4, nq, nbits, nullptr, nullptr, hist);
     hamming_bound_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, kSample, n, k, T);
-    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, T, nullptr, hist);
-    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, T, nullptr, cut, take, redo);
+    count<<<grid, 128, smem, s>>>(c4, 0, n, seg_len, q4, nq, nbits, T, nullptr, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, T, nullptr, cut, take, redo);
     // queries whose bound was short are recounted without a bound (warps without such a query exit at once)
-    count<<<blocks, 128, smem, s>>>(c4, 0, n, q4, nq, nbits, T, redo, hist);
-    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, nq, nbits, k, T, redo, cut, take, nullptr);
+    count<<<grid, 128, smem, s>>>(c4, 0, n, seg_len, q4, nq, nbits, T, redo, hist);
+    hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, T, redo, cut, take, nullptr);
     count_launches(6);
   }
-  emit<<<blocks, 128, smem, s>>>(c4, n, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i);
+  emit<<<grid, 128, smem, s>>>(c4, n, seg_len, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i);
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -286,9 +339,11 @@ int vdb_lsh_encode(const float* x, int64_t n, int d, int64_t ld, const float* pr
 
 size_t vdb_hamming_topk_workspace_bytes(int64_t nq, int nbits) {
   if (nq <= 0 || nbits <= 0) return 0;
-  const size_t a = (static_cast<size_t>(nq) * (nbits + 1) * 4 + 255) & ~size_t(255);
+  const size_t segs = 32;                                     // upper bound of hamming_segments()
+  const size_t a = (segs * static_cast<size_t>(nq) * (nbits + 1) * 4 + 255) & ~size_t(255);
+  const size_t t = (segs * static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
   const size_t b = (static_cast<size_t>(nq) * 4 + 255) & ~size_t(255);
-  return a + 3 * b + ((static_cast<size_t>(nq) + 255) & ~size_t(255));
+  return a + t + 2 * b + ((static_cast<size_t>(nq) + 255) & ~size_t(255));
 }
 
 int vdb_hamming_topk(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(W * 32)
 rerank_topk_kernel(int metric, const float* __restrict__ base, int64_t n, int dpad, int64_t ld,
                    const int64_t* __restrict__ cand, int c, const float* __restrict__ qmat, int64_t ld_q,
                    int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
   int* cnts = reinterpret_cast<int*>(pools + W * CAP);
@@ -58,7 +58,7 @@ template <int KP, int W>
 static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int64_t ld, const int64_t* cand, int64_t nq,
                          int c, const float* q, int64_t ld_q, int k, int flags, float pad_value, float* out_d,
                          int64_t* out_i, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(W) * 2 * KP * 8 + W * 4 + static_cast<size_t>(dpad) * 4;
+  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>(dpad) * 4;
   auto kern = rerank_topk_kernel<KP, W>;
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, c, q, ld_q, k, flags,

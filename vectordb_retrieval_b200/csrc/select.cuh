@@ -6,7 +6,7 @@ namespace vdb {
 
 template <int KP>
 struct WarpTopK {
-  static constexpr int CAP = 2 * KP;
+  static constexpr int CAP = pool_cap(KP);
   static constexpr int E = CAP / 32;
   uint64_t* pool;   // CAP slots, warp-private shared memory
   int cnt;          // warp-uniform
@@ -53,7 +53,7 @@ template <int KP, int W>
 __device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* pools_smem, int* cnts_smem, int warp, int lane,
                                                int metric, int k, int flags, float pad_value, int64_t id_offset,
                                                float* out_d, int64_t* out_i) {
-  constexpr int CAP = 2 * KP;
+  constexpr int CAP = pool_cap(KP);
   constexpr int E = KP / 32;
   if (lane == 0) cnts_smem[warp] = mine.cnt;
   __syncthreads();
