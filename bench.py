@@ -193,10 +193,13 @@ def run_ours(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: anything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("VDB_NCCL_DEBUG", "WARN")   # stdout carries ONE JSON line, nothing else
         dist.init_process_group("nccl", device_id=dev)
 
     from vectordb_retrieval_b200 import _lib, engine, sharded
@@ -204,10 +207,16 @@ def run_ours(args) -> int:
     from vectordb_retrieval_b200.indexes import GpuIndexFlat
     lib = _lib.load()
 
-    plan = sharded.ShardPlan(N_BASE, world)
-    lo, hi = plan.start(rank), plan.stop(rank)
-    rows = _device_rows(lo, hi, dev)
-    index = sharded.DistributedFlatIndex(rows, "l2", dev, id_offset=lo)
+    mode = sharded.choose_sharding(N_BASE, DIM, world, args.shard) if world > 1 else "none"
+    if mode == "queries":        # small base: replicate it, every rank searches nq / world queries
+        lo, hi = 0, N_BASE
+        rows = _device_rows(lo, hi, dev)
+        index = sharded.ReplicatedFlatIndex(rows, "l2", dev)
+    else:                        # north-star layout: row shards, top-k allgather, merge kernel
+        plan = sharded.ShardPlan(N_BASE, world)
+        lo, hi = plan.start(rank), plan.stop(rank)
+        rows = _device_rows(lo, hi, dev)
+        index = sharded.DistributedFlatIndex(rows, "l2", dev, id_offset=lo)
     del rows
     gq = torch.Generator(device=dev).manual_seed(4242)
     q_dev = torch.randn((NQ, DIM), generator=gq, device=dev, dtype=torch.float32)
@@ -294,7 +303,8 @@ def run_ours(args) -> int:
         return 0
 
     peaks = _peaks()
-    flops = 2.0 * NQ * (hi - lo) * DIM                      # per launch on this rank (2 nq N d)
+    nq_launch = (NQ + world - 1) // world if mode == "queries" else NQ
+    flops = 2.0 * nq_launch * (hi - lo) * DIM               # per launch on this rank (2 nq N d)
     pipe_tflops = 3.0 * flops / (scan_ms_mean * 1e-3) / 1e12
     tf32_peak = peaks["bf16_sustained"] / 2.0
     traffic = None
@@ -320,7 +330,9 @@ def run_ours(args) -> int:
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "tf32x3 (fp32-accurate split) + f64 re-score", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": N_BASE, "d": DIM, "nq": NQ, "k": TOPK, "metric": "l2",
-                   "sharding": f"rows/{world}" if world > 1 else "none",
+                   "sharding": ("none" if world == 1 else f"rows/{world}: row shards, NCCL allgather of local top-k, merge kernel"
+                                if mode == "rows" else f"queries/{world}: base replicated ({shard_bytes / 1e9:.2f} GB per GPU), "
+                                "each rank searches nq/N queries, NCCL allgather of the result blocks"),
                    "l2": ("flushed between steps (256 MB write, outside the per-step events)" if flush else
                           f"operands ({shard_bytes / 1e9:.2f} GB per GPU) exceed the 126 MB L2"),
                    "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
@@ -340,6 +352,8 @@ def run_ours(args) -> int:
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,13 +367,16 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--shard", choices=["auto", "rows", "queries"], default="auto",
+                    help="N > 1: 'rows' = north-star row sharding; 'queries' = replicated base; auto picks by base size")
     args = ap.parse_args()
     if args.steps > 500:
         args.steps = 500
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:      # convenience: re-launch one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
+               "--shard", args.shard]
         return subprocess.call(cmd + (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

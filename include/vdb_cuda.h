@@ -114,8 +114,9 @@ int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, in
  * Returns the previous mode. */
 int vdb_set_debug_mode(int mode);
 /* mode 8 (and 9 = 8 with kept bounds): the tcgen05 scan also accumulates epilogue counters; this
- * reads and clears them: [0] epilogue-warp cycles, [1] of which waiting for an accumulator, [2] for
- * norms, [3] appended candidates, [4] compactions (per lane), [5] compaction cycles, [6] warps. */
+ * reads and clears them: [0] epilogue-warp cycles, [1] of which waiting for an accumulator, [2] in
+ * the append path, [3] appended candidates, [4] chunks with a hit in first-generation items and
+ * [5] their cycles, [6] epilogue warps, [7] chunks with a hit. */
 int vdb_debug_read_prof(uint64_t* out8);
 
 /* Measurement hook for bench.py's roofline leg: while enabled, every vdb_flat_topk call brackets

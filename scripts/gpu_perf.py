@@ -45,12 +45,12 @@ if dbg >= 8:
     _ = shard.search(q.clone(), k, 0, 3.4e38, code)
     torch.cuda.synchronize()
     _lib.load().vdb_debug_read_prof(buf)
-    tot, wait, nrm, app, ncomp, ccyc, warps, hits = [int(buf[i]) for i in range(8)]
-    print(f"  hit chunks/warp {hits / max(warps, 1):,.0f}, cycles in hit path {100 * nrm / max(tot, 1):.1f}% = {nrm / max(hits, 1):,.0f} cyc per hit chunk; "
-          f"generation 0: {ncomp / max(warps, 1):,.0f} hit chunks/warp, {100 * ccyc / max(tot, 1):.1f}% of cycles, {ccyc / max(ncomp, 1):,.0f} cyc each")
-    print(f"  prof: epilogue warps {warps}, cycles/warp {tot / max(warps, 1):,.0f}, waiting for MMA {100 * wait / max(tot, 1):.1f}%, "
-          f"for norms {100 * nrm / max(tot, 1):.1f}%, compaction {100 * ccyc / max(tot, 1):.1f}% ({ncomp:,} lane-compactions, "
-          f"{ccyc / max(ncomp, 1) * 1.0:,.0f} cyc each incl. peers), appends {app:,} ({app / nq:,.0f} per query)", flush=True)
+    tot, wait, hitcyc, app, hits0, hitcyc0, warps, hits = [int(buf[i]) for i in range(8)]
+    w = max(warps, 1)
+    print(f"  epilogue warps {warps}: {tot / w:,.0f} cycles each, {100 * wait / max(tot, 1):.1f}% waiting for an accumulator, "
+          f"{100 * hitcyc / max(tot, 1):.1f}% in the append path ({hits / w:,.0f} chunks with a hit per warp, "
+          f"{hitcyc / max(hits, 1):,.0f} cycles each; first-generation items: {hits0 / w:,.0f} chunks, "
+          f"{hitcyc0 / max(hits0, 1):,.0f} cycles each); {app:,} candidates appended ({app / nq:,.0f} per query)", flush=True)
 ms = float(np.median(ts))
 flops = 2.0 * nq * n * d
 print(f"[{impl} dbg={dbg}] n={n} d={d} nq={nq} k={k} {metric}: median {ms:.3f} ms (min {min(ts):.3f})  "

@@ -48,10 +48,11 @@ dist.init_process_group("nccl", device_id=dev)
 import vectordb_retrieval_b200.algorithms as A
 rng = np.random.RandomState(3)
 base = rng.randn(30011, 48).astype(np.float32); queries = rng.randn(257, 48).astype(np.float32)
-algo = A.get_algorithm_instance("ExactSearch", 48, name="dist", metric="l2", device=dev)
-algo.build_index(base)                       # rows sharded over the ranks
-d, i = algo.batch_search(queries, 50)
-np.save(os.path.join({out!r}, f"d{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i{{rank}}.npy"), i)
+for mode in ("rows", "queries"):              # row shards + merge kernel / replicated base + query slices
+    algo = A.get_algorithm_instance("ExactSearch", 48, name="dist", metric="l2", device=dev, shard=mode)
+    algo.build_index(base)
+    d, i = algo.batch_search(queries, 50)
+    np.save(os.path.join({out!r}, f"d_{{mode}}{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i_{{mode}}{{rank}}.npy"), i)
 dist.destroy_process_group()
 """
 
@@ -71,7 +72,10 @@ def test_distributed_flat_index_nccl(tmp_path):
     base = rng.randn(30011, 48).astype(np.float32)
     queries = rng.randn(257, 48).astype(np.float32)
     ref = oracle.faiss_flat_search(base, queries, 50, "l2")
-    for r in range(n):
-        res = oracle.compare_topk(ref[0], ref[1], np.load(tmp_path / f"d{r}.npy"), np.load(tmp_path / f"i{r}.npy"), rtol=1e-5)
-        assert res["ok"], res
-    np.testing.assert_array_equal(np.load(tmp_path / "i0.npy"), np.load(tmp_path / f"i{n - 1}.npy"))
+    for mode in ("rows", "queries"):
+        for r in range(n):
+            res = oracle.compare_topk(ref[0], ref[1], np.load(tmp_path / f"d_{mode}{r}.npy"), np.load(tmp_path / f"i_{mode}{r}.npy"),
+                                      rtol=1e-5)
+            assert res["ok"], (mode, r, res)
+        np.testing.assert_array_equal(np.load(tmp_path / f"i_{mode}0.npy"), np.load(tmp_path / f"i_{mode}{n - 1}.npy"))
+    np.testing.assert_array_equal(np.load(tmp_path / "i_rows0.npy"), np.load(tmp_path / "i_queries0.npy"))

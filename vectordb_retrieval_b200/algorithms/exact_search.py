@@ -8,8 +8,9 @@ Same constructor, same value conventions as the FAISS-backed original:
 * not built -> RuntimeError (exact_search.py:53-54).
 ``faiss.IndexFlat`` becomes :class:`GpuIndexFlat` (tcgen05 3xTF32 contraction fused with the
 per-query top-k bound, exact re-scoring of the winners).  Extra keyword arguments: ``device``
-(one GPU) or ``devices`` (list: row-sharded single-process search); under ``torchrun`` the base is
-row-sharded over the ranks automatically."""
+(one GPU) or ``devices`` (list: row-sharded single-process search); under ``torchrun`` the work is
+split over the ranks: ``shard='rows'`` (row shards + top-k allgather + merge kernel), ``'queries'``
+(replicated base, each rank searches a slice of the batch) or ``'auto'`` (queries while the base is small)."""
 from __future__ import annotations
 
 from typing import Any, Dict, List, Optional, Tuple
@@ -31,7 +32,7 @@ class ExactSearch(BaseAlgorithm):
             raise RuntimeError(f"expected vectors of shape [n, {self.dimension}], got {vectors.shape}")
         self.vectors = vectors          # the harness' array; never mutated (dtype/layout fixed on upload)
         self.index = GpuIndexFlat(self.dimension, self.metric, device=self.config.get("device"),
-                                  devices=self.config.get("devices"))
+                                  devices=self.config.get("devices"), shard=self.config.get("shard", "auto"))
         self.index.add(vectors)
         self.index_built = True
 

@@ -47,8 +47,7 @@ struct FlatScanParams {
   int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
 
-// bring-up counters (vdb_debug_read_prof): epilogue-warp cycles total / waiting for an accumulator /
-// waiting for norms, appended candidates, compaction calls, compaction cycles
+// bring-up counters (vdb_debug_read_prof): see include/vdb_cuda.h for the slots
 __device__ unsigned long long g_prof[8];
 
 namespace tc {

@@ -32,7 +32,8 @@ def _metric_name(metric) -> str:
 class GpuIndexFlat:
     """``faiss.IndexFlat(d, metric)``: exact search on one GPU, or row-sharded over several."""
 
-    def __init__(self, d: int, metric="l2", device=None, devices=None, normalize: bool = False):
+    def __init__(self, d: int, metric="l2", device=None, devices=None, normalize: bool = False, shard: str = "auto"):
+        self.shard = shard                    # under torchrun: 'rows', 'queries' (replicated base) or 'auto'
         self.d = int(d)
         self.metric = _metric_name(metric)
         self.normalize = bool(normalize)      # cosine: rows and queries are L2-normalised on the device
@@ -52,7 +53,9 @@ class GpuIndexFlat:
         from . import sharded
         rank, world = sharded.dist_info()
         metric = "cosine" if self.normalize and self.metric == "ip" else self.metric
-        if world > 1:
+        if world > 1 and sharded.choose_sharding(int(x.shape[0]), (self.d + 31) // 32 * 32, world, self.shard) == "queries":
+            self._impl = sharded.ReplicatedFlatIndex(x, metric, self.device)
+        elif world > 1:
             self._impl = sharded.DistributedFlatIndex.from_global(x, metric, self.device)
         elif self.devices is not None and len(self.devices) > 1:
             self._impl = sharded.MultiDeviceFlatIndex(x, metric, self.devices)

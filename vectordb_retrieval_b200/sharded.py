@@ -127,6 +127,57 @@ class DistributedFlatIndex:
         return eng.merge_topk(d_all, i_all, descending=descending, pad_value=pad_value)
 
 
+class ReplicatedFlatIndex:
+    """Small-base layout: every rank holds the WHOLE base and searches its slice of the query batch;
+    the per-rank result blocks are concatenated with one allgather.  No merge and no top-k exchange:
+    the units that shard are the queries.  Chosen by ``shard="auto"`` when the operands fit a GPU
+    with room to spare - a 1M x 128 base is 1 GB, and cutting it by rows over 8 GPUs leaves each scan
+    125k rows, dominated by fixed costs (bound warm-up, finalize, exchange)."""
+
+    def __init__(self, vectors, metric: str = "l2", device=None, group=None):
+        from . import engine
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = dist_info()
+        self.shard = engine.FlatShard(vectors, metric, device)
+        self.metric = metric
+
+    def memory_bytes(self) -> int:
+        return self.shard.memory_bytes()
+
+    def search(self, q: torch.Tensor, k: int, flags: int = 0, pad_value: Optional[float] = None,
+               impl: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        import torch.distributed as dist
+        eng = self.engine
+        descending = self.metric != "l2" and not (flags & (eng._lib.OUT_NEGATE | eng._lib.OUT_ONE_MINUS))
+        if pad_value is None:
+            pad_value = -eng.FLT_MAX if descending else eng.FLT_MAX
+        nq = q.shape[0]
+        if self.world == 1:
+            return self.shard.search(q, k, flags, pad_value, impl)
+        per = (nq + self.world - 1) // self.world
+        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        d_loc = torch.full((per, k), pad_value, dtype=torch.float32, device=q.device)
+        i_loc = torch.full((per, k), -1, dtype=torch.int64, device=q.device)
+        if hi > lo:
+            self.shard.search(q[lo:hi], k, flags, pad_value, impl, out=(d_loc[: hi - lo], i_loc[: hi - lo]))
+        d_all = torch.empty((self.world * per, k), dtype=torch.float32, device=q.device)
+        i_all = torch.empty((self.world * per, k), dtype=torch.int64, device=q.device)
+        dist.all_gather_into_tensor(d_all, d_loc, group=self.group)
+        dist.all_gather_into_tensor(i_all, i_loc, group=self.group)
+        return d_all[:nq], i_all[:nq]
+
+
+def choose_sharding(n_rows: int, kpad: int, world: int, requested: str = "auto") -> str:
+    """'rows' (north-star layout: row shards + top-k allgather + merge) or 'queries' (replicated base).
+    auto: replicate while the operand set (2 * n * kpad * 4 bytes) stays under 8 GB per GPU."""
+    if requested in ("rows", "queries"):
+        return requested
+    if requested != "auto":
+        raise ValueError(f"shard must be 'auto', 'rows' or 'queries', got '{requested}'")
+    return "queries" if world > 1 and 8.0 * n_rows * kpad <= 8e9 else "rows"
+
+
 class MultiDeviceFlatIndex:
     """Single-process variant for the reference's one-process harness: one FlatShard per visible
     device, queries broadcast with peer copies, local top-k lists copied to the first device and
