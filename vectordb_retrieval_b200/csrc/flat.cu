@@ -48,7 +48,7 @@ static int pick_chunks(int n_qtiles, int n_tiles, int slots, int waves, int max_
 static int max_pools(int64_t nq, int sm) {
   // upper bound of the pools per query over every implementation, independent of the base size
   const int qt128 = static_cast<int>((nq + 127) / 128), qt64 = static_cast<int>((nq + 63) / 64);
-  const int a = (sm / qt128 + 3) * tc::kEpilogueGroups;              // tcgen05: clusters sharing one query tile
+  const int a = sm / qt128 + 3;                                      // tcgen05: lineages of one query tile
   const int b = std::max(1, (2 * sm * 8 + qt64 - 1) / qt64);         // SIMT chunks (slots = 2*sm)
   return std::min(std::max(a, b), 2 * sm) + 2;
 }

@@ -51,8 +51,7 @@ struct FlatScanParams {
 __device__ unsigned long long g_prof[8];
 
 namespace tc {
-constexpr int kEpilogueGroups = 1;                   // groups of four epilogue warps (tiles alternate between groups)
-constexpr int kThreads = 128 + 128 * kEpilogueGroups;
+constexpr int kThreads = 256;
 constexpr int kStages = 3;
 constexpr int kBlockRows = 128;                      // rows per operand block (A or B half)
 constexpr int kBlockBytes = kBlockRows * 128;        // 16 KB: 128 rows x 32 fp32, SWIZZLE_128B
@@ -229,7 +228,6 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // lane beats its bound; only then is the (rare) append code entered.  The chunk loop is a
     // runtime loop over two register buffers so the steady state stays small in the I-cache.
     const int ew = warp & 3;                       // TMEM lane quarter == warp % 4
-    const uint32_t grp = static_cast<uint32_t>(warp - 4) >> 2;   // epilogue group == accumulator buffer it drains
     constexpr int NCH = UMMA_N / 32;               // 32-column chunks per tile
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     uint32_t va[32], vb[32];
@@ -261,7 +259,6 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
-        if (tc::kEpilogueGroups > 1 && buf != grp) continue;   // the other group's tile
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
         const uint32_t thr_seen = ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
         const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;

@@ -85,12 +85,12 @@ ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __re
         const float4 x = __ldg(p + c * 32);
         const float4 y = qs[c];
         if (metric == VDB_METRIC_L2) {
+          // four terms in fp32 (fused multiply-adds), then into the fp64 accumulator: one conversion
+          // per 16 bytes instead of four, relative error of the sum stays ~1e-7
           const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-          acc += static_cast<double>(d0) * d0 + static_cast<double>(d1) * d1 +
-                 static_cast<double>(d2) * d2 + static_cast<double>(d3) * d3;
+          acc += static_cast<double>(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
         } else {
-          acc += static_cast<double>(x.x) * y.x + static_cast<double>(x.y) * y.y +
-                 static_cast<double>(x.z) * y.z + static_cast<double>(x.w) * y.w;
+          acc += static_cast<double>(fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))));
         }
       }
       const bool valid = id >= 0;

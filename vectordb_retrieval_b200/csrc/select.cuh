@@ -58,21 +58,31 @@ __device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* poo
   if (lane == 0) cnts_smem[warp] = mine.cnt;
   __syncthreads();
   if (warp != 0) return;
+  // the W pools are walked as one virtual list, KP entries per merge step: short lists (small
+  // nprobe, few candidates) then cost one or two merges instead of one per warp
   uint64_t best[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) best[e] = kEmpty;
-  for (int w = 0; w < W; ++w) {
-    const int c = cnts_smem[w];
-    const uint64_t* p = pools_smem + w * CAP;
-    for (int base = 0; base < c; base += KP) {
-      uint64_t fresh[E];
+  int start[W + 1];
+  start[0] = 0;
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = base + e * 32 + lane;
-        fresh[e] = i < c ? p[i] : kEmpty;
+  for (int w = 0; w < W; ++w) start[w + 1] = start[w] + cnts_smem[w];
+  const int total = start[W];
+  for (int base = 0; base < total; base += KP) {
+    uint64_t fresh[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int g = base + e * 32 + lane;
+      uint64_t v = kEmpty;
+      if (g < total) {
+        int w = 0;
+#pragma unroll
+        for (int t = 1; t < W; ++t) w += g >= start[t] ? 1 : 0;
+        v = pools_smem[w * CAP + (g - start[w])];
       }
-      warp_merge_keep<E>(best, fresh, lane);
+      fresh[e] = v;
     }
+    warp_merge_keep<E>(best, fresh, lane);
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
