@@ -57,7 +57,8 @@ def _check(ref, got, rtol=1e-5, atol=0.0):
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("metric", ["l2", "ip"])
-@pytest.mark.parametrize("n,d,nq,k", [(5000, 64, 300, 10), (20000, 128, 700, 100), (3000, 50, 64, 200), (4, 2, 2, 2)])
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 64, 300, 10), (20000, 128, 700, 100), (3000, 50, 64, 200), (4, 2, 2, 2),
+                                      (2500, 768, 70, 100), (70000, 1, 33, 504), (1, 5, 3, 4)])
 def test_flat_topk_matches_faiss_flat_oracle(eng, impl, metric, n, d, nq, k):
     from vectordb_retrieval_b200 import _lib
     base, q = _data(n, d, nq, seed=7 * n + d)
@@ -249,3 +250,30 @@ def test_faiss_lsh_pipeline_recall(eng):
         _check(ref, (dist, idx))
         recalls.append(oracle.recall_at_k(gt, idx, 10))
     assert recalls[1] > recalls[0] and recalls[1] > 0.6
+
+
+def test_full_size_c2_properties(eng):
+    """BASELINE.json configs[1] at full size (1M x 128, 10k queries, k=100, L2) through size-independent
+    properties: sorted distances, unique in-range ids, shard-count invariance (3 row shards + merge
+    kernel == 1 shard, bit for bit), and oracle parity on a sample of the queries."""
+    n, d, nq, k = 1_000_000, 128, 10_000, 100
+    g = torch.Generator(device="cuda").manual_seed(42)
+    base = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32)
+    D, I = eng.FlatShard(base, "l2", "cuda").search(q.clone(), k)
+    assert bool((D[:, 1:] >= D[:, :-1]).all()) and int(I.min()) >= 0 and int(I.max()) < n
+    srt = torch.sort(I, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all()), "duplicate ids inside a result row"
+    # shard-count invariance
+    bounds = [0, 333_312, 700_000, n]
+    ds, is_ = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        dd, ii = eng.FlatShard(base[a:b], "l2", "cuda", id_offset=a).search(q.clone(), k)
+        ds.append(dd), is_.append(ii)
+    Dm, Im = eng.merge_topk(torch.stack(ds), torch.stack(is_))
+    assert torch.equal(Im, I) and torch.equal(Dm, D)
+    # oracle on a query sample (fp64 brute force on the host)
+    pick = np.random.RandomState(0).choice(nq, 24, replace=False)
+    ref = oracle.faiss_flat_search(base.cpu().numpy(), q[pick].cpu().numpy(), k, "l2")
+    _check(ref, (D[pick].cpu().numpy(), I[pick].cpu().numpy()))
+    assert oracle.recall_at_k(ref[1], I[pick].cpu().numpy(), k) == 1.0
