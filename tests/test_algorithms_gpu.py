@@ -288,3 +288,58 @@ def test_smoke_config_c1_through_cli_entry(A, tmp_path):
     assert 0.3 < results["ivf_flat"]["recall@10"] <= 1.0
     assert results["faiss_lsh"]["recall@10"] > 0.5 and 0.0 < results["lsh"]["recall@10"] < 1.0
     assert results["exact"]["n_train"] == 10000 and results["exact"]["n_test"] == 100
+
+
+@pytest.mark.parametrize("kind", ["exact", "ivf", "lsh"])
+def test_save_load_index_round_trip_is_bit_identical(A, kind, tmp_path):
+    """save_index / load_index (reference base_algorithm.py:98-120; driver experiment_runner.py:308-344):
+    a reloaded index answers exactly as the one that was saved."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3000, 24)).astype(np.float32)
+    q = rng.standard_normal((37, 24)).astype(np.float32)
+    make = {"exact": lambda: A.ExactSearch("e", 24, metric="l2"),
+            "ivf": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,Flat", metric="l2", nprobe=4),
+            "lsh": lambda: A.ApproximateSearch("h", 24, index_type="LSH", metric="l2")}[kind]
+    a = make()
+    with pytest.raises(RuntimeError):
+        a.save_index(str(tmp_path / "x"))
+    a.build_index(x)
+    d0, i0 = a.batch_search(q, 10)
+    ctx = {"dataset_fingerprint": "fp", "config_hash": "c", "build_metrics": {"build_time_s": 0.25}}
+    info = a.save_index(str(tmp_path / "art"), context=ctx)
+    assert os.path.exists(os.path.join(info["artifact_dir"], "WRITE_COMPLETE"))
+    b = make()
+    loaded = b.load_index(str(tmp_path / "art"), context={"dataset_fingerprint": "fp"})
+    assert loaded["build_time_s"] == 0.25 and b.index_built
+    d1, i1 = b.batch_search(q, 10)
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0, d1)
+    with pytest.raises(RuntimeError):
+        make().load_index(str(tmp_path / "art"), context={"dataset_fingerprint": "another"})
+    with pytest.raises(FileNotFoundError):
+        make().load_index(str(tmp_path / "missing"))
+
+
+def test_harness_persistence_modes(A, tmp_path):
+    """build_only then retrieve_only through the harness reproduces the built run (reference
+    experiment_runner.py:308-372)."""
+    from vectordb_retrieval_b200.harness.config import ExperimentConfig
+    from vectordb_retrieval_b200.harness.experiment_runner import ExperimentRunner
+    art = str(tmp_path / "artifacts")
+
+    def run(mode):
+        cfg = ExperimentConfig(dataset="random", dataset_options={"train_size": 2000, "test_size": 50, "dimensions": 16},
+                               n_queries=50, topk=10,
+                               algorithms={"ivf": {"type": "ApproximateSearch", "index_type": "IVF8,Flat", "nprobe": 8,
+                                                   "persistence": {"enabled": True, "mode": mode, "artifact_dir": art,
+                                                                   "path_policy": "versioned"}}})
+        r = ExperimentRunner(cfg, output_dir=str(tmp_path / mode))
+        r.register_algorithm(A.get_algorithm_instance("ApproximateSearch", 16, name="ivf", index_type="IVF8,Flat", nprobe=8))
+        return r.run()["ivf"]
+
+    with pytest.raises(FileNotFoundError):
+        run("retrieve_only")
+    built = run("build_only")
+    assert built["status"] == "build_only" and built["qps"] == 0.0 and os.path.isdir(built["persist_dir"])
+    loaded = run("retrieve_only")
+    assert loaded["index_source"] == "loaded" and loaded["index_load_time_s"] > 0 and loaded["recall@10"] == 1.0

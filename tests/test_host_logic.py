@@ -154,3 +154,45 @@ def test_reference_registry_plugin_if_reference_present():
     comp = ref_algorithms.get_algorithm_instance("Composite", 8, name="c", indexer={"type": "BruteForceIndexer"},
                                                  searcher={"type": "LinearSearcher"})
     assert isinstance(comp.searcher, A.LinearSearcher)
+
+
+def test_persist_artifact_round_trip_and_guards(tmp_path):
+    """save_index / load_index protocol (reference base_algorithm.py:98-120): sentinel written last,
+    kind / fingerprint mismatches refuse to load, arrays come back bit for bit."""
+    from vectordb_retrieval_b200 import persist
+    rng = np.random.default_rng(0)
+    arrays = {"hi": rng.standard_normal((8, 32)).astype(np.float32), "meta": np.array([5, 3, 0], dtype=np.int64)}
+    ctx = {"dataset_fingerprint": "abc", "config_hash": "h", "build_metrics": {"build_time_s": 1.5}}
+    d = str(tmp_path / "art")
+    info = persist.write_artifact(d, "flat", arrays, {"d": 3}, ctx)
+    assert info["kind"] == "flat" and sorted(info["files"]) == ["hi.npy", "meta.npy"]
+    got, manifest = persist.read_artifact(d, "flat", {"dataset_fingerprint": "abc"})
+    assert manifest["build_metrics"]["build_time_s"] == 1.5 and manifest["meta"] == {"d": 3}
+    for name, arr in arrays.items():
+        assert got[name].dtype == arr.dtype and np.array_equal(got[name], arr)
+    with pytest.raises(RuntimeError):
+        persist.read_artifact(d, "ivf_flat")
+    with pytest.raises(RuntimeError):
+        persist.read_artifact(d, "flat", {"dataset_fingerprint": "other"})
+    os.remove(os.path.join(d, persist.SENTINEL))
+    with pytest.raises(FileNotFoundError):
+        persist.read_artifact(d, "flat")
+    with pytest.raises(FileNotFoundError):
+        persist.read_artifact(str(tmp_path / "absent"), "flat")
+
+
+def test_harness_persistence_config_validation(tmp_path):
+    from vectordb_retrieval_b200.harness.config import ExperimentConfig
+    from vectordb_retrieval_b200.harness.experiment_runner import ExperimentRunner
+    cfg = ExperimentConfig(algorithms={"a": {"type": "ExactSearch", "persistence": {"enabled": True, "mode": "bogus"}},
+                                       "b": {"type": "ExactSearch", "persistence": {"enabled": True, "mode": "Retrieve_Only",
+                                                                                    "path_policy": "versioned"}},
+                                       "c": {"type": "ExactSearch"}})
+    r = ExperimentRunner(cfg, output_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        r._persistence_cfg("a")
+    assert r._persistence_cfg("b")["mode"] == "retrieve_only" and r._persistence_cfg("b")["enabled"]
+    assert r._persistence_cfg("c") == {"mode": "build_and_retrieve", "path_policy": "fixed", "enabled": False}
+    train = np.zeros((4, 3), dtype=np.float32)
+    c1, c2 = r._persistence_context("b", train), r._persistence_context("c", train)
+    assert c1["dataset_fingerprint"] == c2["dataset_fingerprint"] and c1["config_hash"] != c2["config_hash"]

@@ -41,6 +41,22 @@ class ApproximateSearch(BaseAlgorithm):
     def get_memory_usage(self) -> int:
         return 0 if self.index is None else self.index.memory_bytes()
 
+    def save_index(self, artifact_dir: str, context: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        if not self.index_built:
+            raise RuntimeError("Index has not been built yet.")
+        return self.index.save(artifact_dir, context)
+
+    def load_index(self, artifact_dir: str, context: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        from ..indexes import index_factory
+        self.index = index_factory(self.dimension, self.index_type, self.metric, device=self.config.get("device"))
+        manifest = self.index.load(artifact_dir, context)
+        if "nprobe" in self.config:
+            self.index.nprobe = int(self.config["nprobe"])
+        elif "nprobe" in manifest["meta"]:
+            self.index.nprobe = int(manifest["meta"]["nprobe"])
+        self.index_built = True
+        return {"build_time_s": float(manifest.get("build_metrics", {}).get("build_time_s", 0.0) or 0.0), "manifest": manifest}
+
     def search(self, query: np.ndarray, k: int = 10) -> Tuple[np.ndarray, np.ndarray]:
         if not self.index_built:
             raise RuntimeError("Index has not been built yet.")

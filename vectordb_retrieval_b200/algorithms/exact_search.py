@@ -40,6 +40,19 @@ class ExactSearch(BaseAlgorithm):
         """Bytes held in HBM (honoured by the harness' memory estimate, experiment_runner.py:493)."""
         return 0 if self.index is None else self.index.memory_bytes()
 
+    def save_index(self, artifact_dir: str, context: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Persist the device operands (base_algorithm.py:98-109 protocol; see persist.py)."""
+        if not self.index_built:
+            raise RuntimeError("Index has not been built yet.")
+        return self.index.save(artifact_dir, context)
+
+    def load_index(self, artifact_dir: str, context: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        from ..indexes import GpuIndexFlat
+        self.index = GpuIndexFlat(self.dimension, self.metric, device=self.config.get("device"))
+        manifest = self.index.load(artifact_dir, context)
+        self.index_built = True
+        return {"build_time_s": float(manifest.get("build_metrics", {}).get("build_time_s", 0.0) or 0.0), "manifest": manifest}
+
     def search(self, query: np.ndarray, k: int = 10) -> Tuple[np.ndarray, np.ndarray]:
         if not self.index_built:
             raise RuntimeError("Index has not been built yet.")

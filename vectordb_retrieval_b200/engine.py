@@ -139,6 +139,28 @@ class FlatShard:
     def memory_bytes(self) -> int:
         return (self.hi.numel() + self.lo.numel() + self.norms.numel()) * 4
 
+    # ---- persistence: the operands themselves, so a reloaded shard is bit-identical -------------
+    def state(self) -> Dict[str, np.ndarray]:
+        return {"hi": self.hi.cpu().numpy(), "lo": self.lo.cpu().numpy(), "norms": self.norms.cpu().numpy(),
+                "meta": np.array([self.n, self.d, self.id_offset], dtype=np.int64)}
+
+    @classmethod
+    def from_state(cls, state: Dict[str, np.ndarray], metric: str, device=None) -> "FlatShard":
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.n, self.d, self.id_offset = (int(v) for v in state["meta"])
+        self.kpad = self.lib.vdb_flat_kpad(self.d)
+        self.n_pad = self.lib.vdb_flat_npad(self.n)
+        if tuple(state["hi"].shape) != (self.n_pad, self.kpad):
+            raise RuntimeError(f"persisted operands have shape {state['hi'].shape}, expected {(self.n_pad, self.kpad)}")
+        self.hi = torch.from_numpy(np.ascontiguousarray(state["hi"])).to(self.dev)
+        self.lo = torch.from_numpy(np.ascontiguousarray(state["lo"])).to(self.dev)
+        self.norms = torch.from_numpy(np.ascontiguousarray(state["norms"])).to(self.dev)
+        self._ws, self._qbuf = {}, {}
+        return self
+
     def _workspace(self, nq: int, k: int) -> torch.Tensor:
         key = (nq, k)
         ws = self._ws.get(key)
@@ -361,6 +383,27 @@ class IVFShard:
     def memory_bytes(self) -> int:
         return self.list_vecs.numel() * 4 + self.list_ids.numel() * 4 + self.quantizer.memory_bytes()
 
+    def state(self) -> Dict[str, np.ndarray]:
+        return {"centroids": self.centroids.cpu().numpy(), "list_vecs": self.list_vecs.cpu().numpy(),
+                "list_ids": self.list_ids.cpu().numpy(), "blk_off": self.blk_off.cpu().numpy(),
+                "counts": self.counts.cpu().numpy(), "assign": self.assign.cpu().numpy(),
+                "meta": np.array([self.n, self.d, self.id_offset, self.nlist, self.n_blocks], dtype=np.int64)}
+
+    @classmethod
+    def from_state(cls, state: Dict[str, np.ndarray], metric: str, device=None) -> "IVFShard":
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.n, self.d, self.id_offset, self.nlist, self.n_blocks = (int(v) for v in state["meta"])
+        self.d4 = self.lib.vdb_ivf_d4(self.d)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)    # noqa: E731
+        self.centroids = to(state["centroids"])
+        self.list_vecs, self.list_ids, self.blk_off = to(state["list_vecs"]), to(state["list_ids"]), to(state["blk_off"])
+        self.counts, self.assign = to(state["counts"]), to(state["assign"])
+        self.quantizer = FlatShard(self.centroids, "l2" if metric == "l2" else "ip", self.dev)
+        return self
+
     def search(self, q: torch.Tensor, k: int, nprobe: int, flags: int = 0, pad_value: float = FLT_MAX,
                scanned: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         nq = q.shape[0]
@@ -425,6 +468,20 @@ class HammingShard:
 
     def memory_bytes(self) -> int:
         return self.codes.numel() * 4 + self.proj_t.numel() * 4
+
+    def state(self) -> Dict[str, np.ndarray]:
+        return {"codes": self.codes.cpu().numpy(), "proj_t": self.proj_t.cpu().numpy(),
+                "meta": np.array([self.n, self.d, self.id_offset, self.nbits, self.words], dtype=np.int64)}
+
+    @classmethod
+    def from_state(cls, state: Dict[str, np.ndarray], device=None) -> "HammingShard":
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.n, self.d, self.id_offset, self.nbits, self.words = (int(v) for v in state["meta"])
+        self.codes = torch.from_numpy(np.ascontiguousarray(state["codes"])).to(self.dev)
+        self.proj_t = torch.from_numpy(np.ascontiguousarray(state["proj_t"])).to(self.dev)
+        return self
 
     def encode(self, x: torch.Tensor) -> torch.Tensor:
         out = torch.zeros((x.shape[0], self.words), dtype=torch.int32, device=self.dev)

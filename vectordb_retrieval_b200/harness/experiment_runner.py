@@ -8,9 +8,14 @@ result are consumed, the batch API falling back to per-query ``search`` on the s
 exception types, and the metric key names of the result JSON.  Added: one untimed warm-up
 ``batch_search`` of a single query when ``warmup`` is set (the reference times the very first
 call, which on a GPU would charge context creation to the first batch), and a ``roofline`` block
-when the algorithm exposes ``last_kernel_ms``.  Persistence modes and plots are out of scope."""
+when the algorithm exposes ``last_kernel_ms``.  The per-algorithm ``persistence`` block
+(``enabled, mode {build_only, retrieve_only, build_and_retrieve}, artifact_dir, path_policy
+{fixed, versioned}, version_tag, fail_if_missing``; reference :163-186, 242-372) drives the
+``save_index / load_index`` protocol.  Plots are out of scope."""
 from __future__ import annotations
 
+import copy
+import hashlib
 import json
 import logging
 import os
@@ -87,11 +92,84 @@ class ExperimentRunner:
                 pass
         return float(train.shape[0]) * train.shape[1] * 4 / (1024.0 * 1024.0)
 
-    def _run_single_algorithm(self, name: str, algorithm: BaseAlgorithm, train: np.ndarray, queries: np.ndarray
-                              ) -> Tuple[Dict[str, Any], np.ndarray, np.ndarray]:
+    # ---- persistence (reference: experiment_runner.py:163-186, 242-257, 267-372) -----------------
+    def _persistence_cfg(self, name: str) -> Dict[str, Any]:
+        raw = self.config.algorithms.get(name, {})
+        raw = raw.get("persistence", {}) if isinstance(raw, dict) else {}
+        if not isinstance(raw, dict):
+            return {}
+        cfg = copy.deepcopy(raw)
+        cfg["mode"] = str(cfg.get("mode", "build_and_retrieve")).strip().lower()
+        if cfg["mode"] not in ("build_only", "retrieve_only", "build_and_retrieve"):
+            raise ValueError(f"Unsupported persistence mode '{cfg['mode']}'")
+        cfg["path_policy"] = str(cfg.get("path_policy", "fixed")).strip().lower()
+        if cfg["path_policy"] not in ("fixed", "versioned"):
+            raise ValueError(f"Unsupported persistence path_policy '{cfg['path_policy']}'")
+        cfg["enabled"] = bool(cfg.get("enabled", False))
+        return cfg
+
+    @staticmethod
+    def _stable_hash(payload: Any) -> str:
+        return hashlib.sha256(json.dumps(payload, sort_keys=True, default=str).encode()).hexdigest()[:16]
+
+    def _persistence_context(self, name: str, train: np.ndarray) -> Dict[str, Any]:
+        algo_cfg = copy.deepcopy(self.config.algorithms.get(name, {}))
+        if isinstance(algo_cfg, dict):
+            algo_cfg.pop("persistence", None)
+        fp_payload = {"dataset": self.config.dataset, "dataset_options": self.config.dataset_options,
+                      "n_train": int(train.shape[0]), "dimensions": int(train.shape[1]), "dtype": str(train.dtype)}
+        return {"dataset_fingerprint": self._stable_hash(fp_payload), "dataset_fingerprint_payload": fp_payload,
+                "config_hash": self._stable_hash({"algorithm_name": name, "algorithm_config": algo_cfg, **fp_payload}),
+                "force_rebuild": False}
+
+    def _build_or_load(self, name: str, algorithm: BaseAlgorithm, train: np.ndarray) -> Dict[str, Any]:
+        pcfg = self._persistence_cfg(name)
+        info: Dict[str, Any] = {"build_time_s": 0.0, "index_load_time_s": 0.0, "index_source": "built"}
+        if not pcfg.get("enabled"):
+            t0 = time.time()
+            algorithm.build_index(train)
+            info["build_time_s"] = time.time() - t0
+            return info
+        ctx = self._persistence_context(name, train)
+        ctx["force_rebuild"] = bool(pcfg.get("force_rebuild", False))
+        if not pcfg.get("artifact_dir"):
+            raise ValueError(f"Algorithm '{name}' has persistence enabled but no persistence.artifact_dir configured.")
+        pdir = str(pcfg["artifact_dir"])
+        if pcfg["path_policy"] == "versioned":
+            tag = pcfg.get("version_tag")
+            pdir = os.path.join(pdir, str(tag).strip() if tag else ctx["dataset_fingerprint"])
+        info.update(persistence_mode=pcfg["mode"], persist_dir=pdir, dataset_fingerprint=ctx["dataset_fingerprint"],
+                    config_hash=ctx["config_hash"])
+        if pcfg["mode"] == "retrieve_only" and os.path.isdir(pdir):
+            t0 = time.time()
+            loaded = algorithm.load_index(pdir, context=ctx)
+            info["index_load_time_s"] = time.time() - t0
+            info["index_source"] = "loaded"
+            info["build_time_s"] = float(loaded.get("build_time_s", 0.0) or 0.0)
+            return info
+        if pcfg["mode"] == "retrieve_only" and pcfg.get("fail_if_missing", True):
+            raise FileNotFoundError(f"Missing persisted index for '{name}' at {pdir}. "
+                                    "Run build_only (or build_and_retrieve) first to create the artifact.")
         t0 = time.time()
         algorithm.build_index(train)
-        build_time = time.time() - t0
+        info["build_time_s"] = time.time() - t0
+        if pcfg["mode"] in ("build_only", "build_and_retrieve"):
+            ctx["build_metrics"] = {"build_time_s": float(info["build_time_s"]), "n_train": int(train.shape[0]),
+                                    "dimensions": int(train.shape[1]), "timestamp": datetime.now().isoformat()}
+            algorithm.save_index(pdir, context=ctx)
+        return info
+
+    def _run_single_algorithm(self, name: str, algorithm: BaseAlgorithm, train: np.ndarray, queries: np.ndarray
+                              ) -> Tuple[Dict[str, Any], Optional[np.ndarray], Optional[np.ndarray]]:
+        pinfo = self._build_or_load(name, algorithm, train)
+        build_time = pinfo["build_time_s"]
+        if pinfo.get("persistence_mode") == "build_only":
+            out = {"algorithm": name, "parameters": algorithm.get_parameters(), "dataset": self.config.dataset,
+                   "n_train": int(train.shape[0]), "n_test": int(len(queries)), "dimensions": int(train.shape[1]),
+                   "topk": self.config.topk, "index_memory_mb": self._memory_mb(algorithm, train), "qps": 0.0,
+                   "mean_query_time_ms": 0.0, "total_query_time_s": 0.0, "status": "build_only",
+                   "timestamp": datetime.now().isoformat(), **pinfo}
+            return out, None, None
         k = self.config.topk
         nq = len(queries)
         indices = np.full((nq, k), -1, dtype=np.int64)
@@ -140,9 +218,9 @@ class ExperimentRunner:
             "qps": float(nq / total) if total > 0 else 0.0,
             "mean_query_time_ms": float(total / max(nq, 1) * 1000.0),
             "total_query_time_s": float(total),
-            "index_source": "built",
             "timestamp": datetime.now().isoformat(),
         }
+        out.update({key: v for key, v in pinfo.items() if key != "build_time_s"})
         ops = algorithm.get_operations()
         if ops:
             out["operations"] = ops
@@ -162,7 +240,8 @@ class ExperimentRunner:
         for name, algorithm in self.algorithms.items():
             metrics, idx, times = self._run_single_algorithm(name, algorithm, train, test)
             self.results[name] = metrics
-            outputs[name] = (idx, times)
+            if idx is not None:
+                outputs[name] = (idx, times)
         if gt is not None:
             for name, (idx, times) in outputs.items():
                 ev = M.evaluate(gt, idx, times)

@@ -72,6 +72,24 @@ class GpuIndexFlat:
     def memory_bytes(self) -> int:
         return 0 if self._impl is None else self._impl.memory_bytes()
 
+    def save(self, artifact_dir: str, context=None):
+        from . import persist
+        if not isinstance(self._impl, engine.FlatShard):
+            raise NotImplementedError("only a single-GPU flat index can be persisted")
+        meta = {"d": self.d, "metric": self.metric, "normalize": self.normalize, "ntotal": self.ntotal}
+        return persist.write_artifact(artifact_dir, "flat", self._impl.state(), meta, context)
+
+    def load(self, artifact_dir: str, context=None):
+        from . import persist
+        arrays, manifest = persist.read_artifact(artifact_dir, "flat", context)
+        meta = manifest["meta"]
+        if int(meta["d"]) != self.d or meta["metric"] != self.metric or bool(meta["normalize"]) != self.normalize:
+            raise RuntimeError(f"persisted flat index {meta} does not match d={self.d} metric={self.metric}")
+        dev = self.device if self.device is not None else (self.devices[0] if self.devices else None)
+        self._impl = engine.FlatShard.from_state(arrays, "cosine" if self.normalize and self.metric == "ip" else self.metric, dev)
+        self.ntotal = int(meta["ntotal"])
+        return manifest
+
     def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._impl is None:
             raise RuntimeError("index is empty")
@@ -137,6 +155,25 @@ class GpuIndexIVFFlat:
     def memory_bytes(self) -> int:
         return 0 if self._impl is None else self._impl.memory_bytes()
 
+    def save(self, artifact_dir: str, context=None):
+        from . import persist
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        meta = {"d": self.d, "nlist": self.nlist, "metric": self.metric, "normalize": self.normalize,
+                "nprobe": int(self.nprobe), "ntotal": self.ntotal}
+        return persist.write_artifact(artifact_dir, "ivf_flat", self._impl.state(), meta, context)
+
+    def load(self, artifact_dir: str, context=None):
+        from . import persist
+        arrays, manifest = persist.read_artifact(artifact_dir, "ivf_flat", context)
+        meta = manifest["meta"]
+        if int(meta["d"]) != self.d or int(meta["nlist"]) != self.nlist or meta["metric"] != self.metric:
+            raise RuntimeError(f"persisted IVF index {meta} does not match d={self.d} nlist={self.nlist} metric={self.metric}")
+        self._impl = engine.IVFShard.from_state(arrays, self._engine_metric(), self.device)
+        self.centroids = arrays["centroids"]
+        self.is_trained, self.ntotal = True, int(meta["ntotal"])
+        return manifest
+
     def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._impl is None:
             raise RuntimeError("index is empty")
@@ -186,6 +223,24 @@ class GpuIndexLSH:
 
     def memory_bytes(self) -> int:
         return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def save(self, artifact_dir: str, context=None):
+        from . import persist
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        arrays = dict(self._impl.state(), projection=self.projection)
+        return persist.write_artifact(artifact_dir, "lsh", arrays, {"d": self.d, "nbits": self.nbits, "ntotal": self.ntotal}, context)
+
+    def load(self, artifact_dir: str, context=None):
+        from . import persist
+        arrays, manifest = persist.read_artifact(artifact_dir, "lsh", context)
+        meta = manifest["meta"]
+        if int(meta["d"]) != self.d or int(meta["nbits"]) != self.nbits:
+            raise RuntimeError(f"persisted LSH index {meta} does not match d={self.d} nbits={self.nbits}")
+        self.projection = arrays.pop("projection")
+        self._impl = engine.HammingShard.from_state(arrays, self.device)
+        self.ntotal = int(meta["ntotal"])
+        return manifest
 
     def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._impl is None:
