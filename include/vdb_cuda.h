@@ -119,6 +119,15 @@ int vdb_set_debug_mode(int mode);
  * [5] their cycles, [6] epilogue warps, [7] chunks with a hit. */
 int vdb_debug_read_prof(uint64_t* out8);
 
+/* Seeded bounds of the tcgen05 scan (see flat.cu): a pre-pass over `sample_tiles` strided base
+ * tiles (256 rows each; 0 disables seeding) gives every query the `rank`-th smallest sampled key
+ * as its starting bound; queries whose guess turns out too tight are detected after the main pass
+ * and re-scanned from an infinite bound, so results never depend on these knobs.  Defaults 64, 16.
+ * Debug mode 6 forces every query through the re-scan (test hook), mode 7 disables seeding. */
+int vdb_flat_set_seeding(int sample_tiles, int rank);
+/* Number of queries re-scanned since the last call (reads and clears a device counter). */
+int vdb_debug_redo_queries(uint64_t* out);
+
 /* Measurement hook for bench.py's roofline leg: while enabled, every vdb_flat_topk call brackets
  * its scan kernel with a pair of CUDA events on the launching stream (up to 512 calls).
  * vdb_flat_timing_read waits for the recorded events, writes the scan durations in milliseconds

@@ -26,6 +26,9 @@ code = _lib.IMPL_NAMES[impl]
 dbg = int(os.environ.get("VDB_DBG", "0"))
 if dbg:
     _lib.load().vdb_set_debug_mode(dbg)
+if os.environ.get("VDB_SEED"):                      # "sample_tiles,rank" of the seeding pre-pass (0 tiles = off)
+    _t, _r = (int(v) for v in os.environ["VDB_SEED"].split(","))
+    assert _lib.load().vdb_flat_set_seeding(_t, _r) == 0
 for _ in range(2):
     D, I = shard.search(q.clone(), k, 0, 3.4e38, code)
 torch.cuda.synchronize()
@@ -51,6 +54,11 @@ if dbg >= 8:
           f"{100 * hitcyc / max(tot, 1):.1f}% in the append path ({hits / w:,.0f} chunks with a hit per warp, "
           f"{hitcyc / max(hits, 1):,.0f} cycles each; first-generation items: {hits0 / w:,.0f} chunks, "
           f"{hitcyc0 / max(hits0, 1):,.0f} cycles each); {app:,} candidates appended ({app / nq:,.0f} per query)", flush=True)
+import ctypes as _ct
+_redo = _ct.c_uint64(0)
+_lib.load().vdb_debug_redo_queries(_ct.byref(_redo))
+if _redo.value:
+    print(f"  queries re-scanned over all calls: {_redo.value}")
 ms = float(np.median(ts))
 flops = 2.0 * nq * n * d
 print(f"[{impl} dbg={dbg}] n={n} d={d} nq={nq} k={k} {metric}: median {ms:.3f} ms (min {min(ts):.3f})  "

@@ -277,3 +277,77 @@ def test_full_size_c2_properties(eng):
     ref = oracle.faiss_flat_search(base.cpu().numpy(), q[pick].cpu().numpy(), k, "l2")
     _check(ref, (D[pick].cpu().numpy(), I[pick].cpu().numpy()))
     assert oracle.recall_at_k(ref[1], I[pick].cpu().numpy(), k) == 1.0
+
+
+# ---- seeded bounds: pre-pass guess, verification, redo (flat.cu) -------------------------------
+def _redo_count():
+    import ctypes
+    from vectordb_retrieval_b200 import _lib
+    out = ctypes.c_uint64(0)
+    assert _lib.load().vdb_debug_redo_queries(ctypes.byref(out)) == 0
+    return int(out.value)
+
+
+@pytest.mark.parametrize("metric,n,d,nq,k", [("l2", 140000, 32, 300, 100), ("ip", 40000, 48, 70, 10), ("l2", 300000, 16, 40, 200)])
+def test_seeded_bounds_do_not_change_results(eng, metric, n, d, nq, k):
+    """Shards large enough for the seeding pre-pass: same answer with the pre-pass (default), without
+    it (mode 7) and with every query forced through the redo pass (mode 6); all equal the oracle."""
+    from vectordb_retrieval_b200 import _lib
+    lib = _lib.load()
+    base, q = _data(n, d, nq, seed=n + k)
+    shard = eng.FlatShard(base, metric, "cuda")
+    pad = oracle.FLT_MAX if metric == "l2" else -oracle.FLT_MAX
+    ref = oracle.faiss_flat_search(base, q, k, metric)
+    atol = 0.0 if metric == "l2" else 1e-5 * float(np.linalg.norm(base, axis=1).max() * np.linalg.norm(q, axis=1).max())
+    outs = {}
+    _redo_count()
+    try:
+        for mode in (0, 7, 6):
+            lib.vdb_set_debug_mode(mode)
+            D, I = shard.search(torch.from_numpy(q).cuda(), k, 0, pad)
+            torch.cuda.synchronize()
+            outs[mode] = (D.cpu().numpy(), I.cpu().numpy())
+            redo = _redo_count()
+            if mode == 6:
+                assert redo == nq, f"forced redo touched {redo} of {nq} queries"
+            if mode == 7:
+                assert redo == 0
+    finally:
+        lib.vdb_set_debug_mode(0)
+    for mode, got in outs.items():
+        _check(ref, got, atol=atol)
+        np.testing.assert_array_equal(got[1], outs[0][1])
+        np.testing.assert_array_equal(got[0], outs[0][0])
+
+
+def test_seeded_bounds_misleading_sample_takes_the_redo_pass(eng):
+    """Adversarial row order: the sampled tiles hold only rows close to the queries, so the guessed
+    bound is far too tight for the rest of the base.  The verify kernel must catch those queries and
+    the redo pass must still return the exact answer."""
+    n, d, nq, k = 262144, 32, 64, 100          # 1024 tiles; k' = 128 -> 16 sampled tiles, stride 64
+    rng = np.random.RandomState(3)
+    q = rng.randn(nq, d).astype(np.float32)
+    # (a) guesses far too loose: the sampled tiles hold only far rows -> slower, never wrong, no redo
+    base = rng.randn(n, d).astype(np.float32)
+    for t in range(0, 1024, 64):
+        base[t * 256:(t + 1) * 256] += 50.0
+    shard = eng.FlatShard(base, "l2", "cuda")
+    _redo_count()
+    D, I = shard.search(torch.from_numpy(q).cuda(), k)
+    torch.cuda.synchronize()
+    assert _redo_count() == 0
+    ref = oracle.faiss_flat_search(base, q, k, "l2")
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
+    # (b) guesses far too tight: the only near rows of the base sit in the sampled tiles (5 per tile),
+    # so the 16th smallest sampled key has just 15 rows of the whole base below it
+    base2 = (rng.randn(n, d) * 0.5 + 20.0).astype(np.float32)
+    base2[:, 0] += np.linspace(0.0, 30.0, n, dtype=np.float32)      # far rows drift away with the row number
+    for t in range(0, 1024, 64):
+        base2[t * 256:t * 256 + 5] = rng.randn(5, d).astype(np.float32)
+    shard = eng.FlatShard(base2, "l2", "cuda")
+    D, I = shard.search(torch.from_numpy(q).cuda(), k)
+    torch.cuda.synchronize()
+    redo = _redo_count()
+    ref = oracle.faiss_flat_search(base2, q, k, "l2")
+    _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
+    assert redo > 0, "expected the misleading sample to force at least one query through the redo pass"

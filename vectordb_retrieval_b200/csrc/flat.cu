@@ -82,6 +82,27 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int kpad, int sm)
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static int g_debug_mode = 0;
 
+// Seeded bounds (tcgen05 path, large shards).  A lineage that starts with an infinite bound accepts
+// every key until its pool has seen ~k'/p rows for a hit rate p - roughly the first 200k rows of
+// every lineage are epilogue-bound.  So a pre-pass scans a strided sample of S base tiles (kSeed
+// variant of the scan kernel: no pools, just the smallest chunk minima per query in registers) and
+// takes about the r-th smallest sampled key of every query as that query's *guess* tau (expected
+// rank in the whole shard: r * N / S); the main pass starts from tau, so hits are rare from the
+// first tile on.  tau is not a proven bound: the verify kernel counts the candidates of
+// every query after the main pass, and a query with fewer than k' of them (tau was too tight) is
+// reset and re-scanned from an infinite bound by a third launch that skips every query tile
+// without such a query (normally all of them).  S is capped so that r * N / S >= margin * k':
+// for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) ~ 1e-10.
+static int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
+static int g_pre_rank = 16;      // r (1..32)
+__device__ unsigned long long g_redo_queries;
+
+struct PrePlan {
+  bool on;
+  int stride;          // sampled tile t is base tile t * stride
+  FlatPlan plan;       // decomposition of the sample
+};
+
 // bench.py's roofline leg: scan-kernel durations measured with CUDA events on the launching stream
 constexpr int kTimingSlots = 512;
 static bool g_timing_on = false;
@@ -91,11 +112,77 @@ static bool g_ev_made = false;
 
 // --------------------------------------------------------------------------------------------
 __global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int* handover,
-                                 int64_t n_hand, int keep_thr) {
+                                 int64_t n_hand, int keep_thr, int* active, int64_t n_active) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < nq_pad && !keep_thr) thr[i] = f2ord(CUDART_INF_F);
   if (i < n_cnt) pool_cnt[i] = 0;
   if (i < n_hand) handover[i] = 0;
+  if (i < n_active) active[i] = 0;
+}
+
+static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, int kpad, int sm, int kp) {
+  PrePlan pp{};
+  if (main_plan.cta_group == 0 || g_pre_tiles <= 0) return pp;
+  const int r = std::min(std::max(g_pre_rank, 1), kSeedKeep);
+  const int margin = std::max(4, 128 / r);
+  const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
+  const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
+  if (s_tiles < 8) return pp;                       // small shard: the sample would not pay for itself
+  pp.on = true;
+  pp.stride = main_plan.n_tiles / s_tiles;
+  pp.plan = make_plan(impl, nq, static_cast<int64_t>(s_tiles) * main_plan.tile_rows, kpad, sm);
+  return pp;
+}
+
+// tau[q] = the `rank`-th smallest of the chunk minima the pre-pass kept for query q (kSeedKeep per
+// item, so the union holds the kSeedKeep smallest of the whole sample), as the ordered-uint image
+// the scan compares with.  A chunk minimum is a real key, so tau's rank among the sampled rows is
+// at least `rank`: slightly looser than the exact order statistic, never tighter.
+__global__ void __launch_bounds__(128)
+flat_tau_kernel(const float* __restrict__ seed, int n_chunks, int64_t nq, int rank, int force_fail,
+                uint32_t* __restrict__ thr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (q >= nq) return;
+  const int total = n_chunks * kSeedKeep;
+  const float* v = seed + q * total;
+  uint64_t best[1] = {kEmpty};
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    uint64_t fresh[1] = {i < total ? pack_key(__ldcg(v + i), static_cast<uint32_t>(i)) : kEmpty};
+    warp_merge_keep<1>(best, fresh, lane);
+  }
+  const uint64_t w = __shfl_sync(0xffffffffu, best[0], rank - 1);
+  if (lane == 0) {
+    uint32_t t = w == kEmpty ? f2ord(CUDART_INF_F) : static_cast<uint32_t>(w >> 32);
+    if (force_fail) t = f2ord(-CUDART_INF_F);       // test hook: every query must take the redo pass
+    thr[q] = t;
+  }
+}
+
+// After the main pass: a query whose pools hold fewer than kp candidates in total was started from
+// too tight a guess.  Such queries are reset (empty pools, infinite bound) and their query tile is
+// flagged for the redo pass; every other query gets the bound -inf, so the redo pass - which runs
+// whole query tiles - cannot append to its pools again.
+__global__ void flat_verify_kernel(int* pool_cnt, int n_pools, int64_t nq, int64_t nq_pad, int kp, int tile_rows,
+                                   uint32_t* thr, int* qtile_active, int* handover, int64_t n_hand) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n_hand) handover[i] = 0;
+  if (i >= nq_pad) return;
+  bool failed = false;
+  if (i < nq) {
+    int total = 0;
+    for (int s = 0; s < n_pools; ++s) total += pool_cnt[i * n_pools + s];
+    failed = total < kp;
+  }
+  if (failed) {
+    for (int s = 0; s < n_pools; ++s) pool_cnt[i * n_pools + s] = 0;
+    thr[i] = f2ord(CUDART_INF_F);
+    qtile_active[i / tile_rows] = 1;
+    atomicAdd(&g_redo_queries, 1ull);
+  } else {
+    thr[i] = f2ord(-CUDART_INF_F);
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -361,10 +448,10 @@ static int make_operand_map(CUtensorMap* map, const float* ptr, int64_t rows, in
   return 0;
 }
 
-template <int CG, bool ARES, int KP, bool DENSE>
+template <int CG, bool ARES, int KP, bool DENSE, bool SEED = false>
 static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mbh, const CUtensorMap& mbl,
                      const FlatScanParams& P, int clusters, cudaStream_t stream) {
-  auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE>;
+  auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE, SEED>;
   constexpr int smem = tc::smem_bytes<ARES>();
   static bool configured[64] = {};
   int dev = 0;
@@ -404,6 +491,15 @@ static int run_scan(int impl, const float* hi, const float* lo, int64_t n_pad, i
       make_operand_map(&mbh, hi, n_pad, kpad) || make_operand_map(&mbl, lo, n_pad, kpad))
     return 3;
   const bool ares = P.kb <= tc::kMaxResidentKb;
+  if constexpr (KP == 32) {   // the seeding pre-pass is instantiated once, under the smallest pool size
+    if (P.seed_out != nullptr) {
+      if (plan.cta_group == 2)
+        return ares ? launch_tc<2, true, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                    : launch_tc<2, false, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+      return ares ? launch_tc<1, true, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                  : launch_tc<1, false, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+    }
+  }
   if constexpr (KP == 32) {   // the dense-key test hook exists for the smallest pool size only
     if (P.dense != nullptr) {
       if (plan.cta_group == 2)
@@ -431,12 +527,19 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   const int kpad = vdb_flat_kpad(d);
   const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
   const FlatPlan plan = make_plan(impl, nq, n_pad, kpad, sm);
+  PrePlan pre{};
+  if (dense == nullptr && g_debug_mode != 5 && g_debug_mode != 9 && g_debug_mode != 7)
+    pre = make_pre_plan(impl, nq, plan, kpad, sm, KP);
   constexpr int CAP = pool_cap(KP);
   const size_t off_cnt = align256(static_cast<size_t>(nq_pad) * 4);
   const size_t off_hand = off_cnt + align256(static_cast<size_t>(nq_pad) * plan.n_pools * 4);
   const size_t off_pool = off_hand + align256(static_cast<size_t>(plan.n_qtiles + 1) * plan.n_pools * 4);
   const size_t off_trash = off_pool + static_cast<size_t>(nq_pad) * plan.n_pools * CAP * 8;
-  const size_t need = off_trash + static_cast<size_t>(nq_pad) * 8;
+  size_t need = align256(off_trash + static_cast<size_t>(nq_pad) * 8);
+  // seeding region: [kept chunk minima nq_pad x n_chunks x kSeedKeep f32][query-tile flags of the redo pass]
+  const size_t off_seed = need;
+  const size_t off_act = off_seed + align256(static_cast<size_t>(nq_pad) * (pre.on ? pre.plan.n_chunks : 0) * kSeedKeep * 4);
+  if (pre.on) need = off_act + align256(static_cast<size_t>(plan.n_qtiles + 1) * 4);
   VDB_REQUIRE(ws != nullptr && ws_bytes >= need, "vdb_flat_topk: workspace too small (%zu < %zu)", ws_bytes, need);
   uint8_t* w = static_cast<uint8_t*>(ws);
   FlatScanParams P{};
@@ -448,17 +551,49 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   P.pool_cnt = reinterpret_cast<int*>(w + off_cnt);
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
   P.dense = dense; P.dense_ld = n_pad; P.dbg = g_debug_mode;
+  P.tile_stride = 1; P.qtile_active = nullptr; P.seed_out = nullptr;
+  int* qtile_active = pre.on ? reinterpret_cast<int*>(w + off_act) : nullptr;
   const int64_t n_cnt = nq_pad * plan.n_pools;
   const int64_t n_hand = static_cast<int64_t>(plan.n_qtiles + 1) * plan.n_pools;
+  const int64_t n_act = pre.on ? plan.n_qtiles + 1 : 0;
   flat_init_kernel<<<static_cast<unsigned>((std::max(n_cnt, n_hand) + 255) / 256), 256, 0, stream>>>(
-      P.thr, nq_pad, P.pool_cnt, n_cnt, P.handover, n_hand, g_debug_mode == 5 || g_debug_mode == 9);
+      P.thr, nq_pad, P.pool_cnt, n_cnt, P.handover, n_hand, g_debug_mode == 5 || g_debug_mode == 9, qtile_active, n_act);
   VDB_CHECK_CUDA(cudaGetLastError());
+  int launches = 2 + (out_d != nullptr ? 1 : 0);
+  if (pre.on) {
+    // pre-pass over the strided sample, then tau -> the main pass's starting bounds
+    FlatScanParams Q = P;
+    Q.n_tiles = pre.plan.n_tiles; Q.tiles_per_chunk = pre.plan.tiles_per_chunk; Q.n_chunks = pre.plan.n_chunks;
+    Q.n_pools = pre.plan.n_pools; Q.tile_stride = pre.stride;
+    Q.seed_out = reinterpret_cast<float*>(w + off_seed);
+    Q.dbg = 0;
+    const int rc0 = run_scan<32>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, pre.plan, Q, sm, stream);
+    if (rc0) return rc0;
+    flat_tau_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
+        Q.seed_out, Q.n_chunks, nq, std::min(std::max(g_pre_rank, 1), kSeedKeep), g_debug_mode == 6, P.thr);
+    VDB_CHECK_CUDA(cudaGetLastError());
+    launches += 2;
+  }
   const bool timed = g_timing_on && g_timing_n < kTimingSlots;
   if (timed) VDB_CHECK_CUDA(cudaEventRecord(g_ev0[g_timing_n], stream));
   const int rc = run_scan<KP>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, plan, P, sm, stream);
   if (rc) return rc;
   if (timed) VDB_CHECK_CUDA(cudaEventRecord(g_ev1[g_timing_n++], stream));
-  count_launches(2 + (out_d != nullptr ? 1 : 0));
+  if (pre.on) {
+    // verify the guesses; re-scan the query tiles that hold a failed query (normally none: the
+    // third launch then finds every tile unflagged and returns)
+    flat_verify_kernel<<<static_cast<unsigned>((std::max(nq_pad, n_hand) + 255) / 256), 256, 0, stream>>>(
+        P.pool_cnt, plan.n_pools, nq, nq_pad, static_cast<int>(std::min<int64_t>(KP, n)), plan.tile_rows, P.thr,
+        qtile_active, P.handover, n_hand);
+    VDB_CHECK_CUDA(cudaGetLastError());
+    FlatScanParams R = P;
+    R.qtile_active = qtile_active;
+    R.dbg = 0;
+    const int rc2 = run_scan<KP>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, plan, R, sm, stream);
+    if (rc2) return rc2;
+    launches += 2;
+  }
+  count_launches(launches);
   if (out_d != nullptr) {
     flat_finalize_kernel<KP><<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
         metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, plan.n_pools, P.pools, P.pool_cnt, k, flags, pad_value,
@@ -486,6 +621,21 @@ int vdb_debug_read_prof(uint64_t* out8) {
   for (int i = 0; i < 8; ++i) out8[i] = h[i];
   unsigned long long z[8] = {};
   VDB_CHECK_CUDA(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+  return 0;
+}
+
+int vdb_flat_set_seeding(int sample_tiles, int rank) {
+  VDB_REQUIRE(sample_tiles >= 0 && rank >= 1 && rank <= kSeedKeep, "vdb_flat_set_seeding: sample_tiles >= 0, 1 <= rank <= %d", kSeedKeep);
+  g_pre_tiles = sample_tiles;
+  g_pre_rank = rank;
+  return 0;
+}
+
+int vdb_debug_redo_queries(uint64_t* out) {
+  unsigned long long h = 0, z = 0;
+  VDB_CHECK_CUDA(cudaMemcpyFromSymbol(&h, g_redo_queries, sizeof(h)));
+  VDB_CHECK_CUDA(cudaMemcpyToSymbol(g_redo_queries, &z, sizeof(z)));
+  *out = h;
   return 0;
 }
 
@@ -520,9 +670,15 @@ size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   if (kp == 0 || nq <= 0) return 0;
   const int64_t nq_pad = vdb_flat_nqpad(nq);
   const int s = max_pools(nq, sm);
-  return align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
-         align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) + static_cast<size_t>(nq_pad) * s * pool_cap(kp) * 8 +
-         static_cast<size_t>(nq_pad) * 8 + 256;
+  const size_t main_part = align256(static_cast<size_t>(nq_pad) * 4) + align256(static_cast<size_t>(nq_pad) * s * 4) +
+                           align256(static_cast<size_t>(nq_pad / 64 + 2) * s * 4) +
+                           static_cast<size_t>(nq_pad) * s * pool_cap(kp) * 8 + align256(static_cast<size_t>(nq_pad) * 8);
+  // seeding pre-pass: kSeedKeep chunk minima per (query, item of the sample), plus the redo pass's tile flags
+  const int64_t qt_min = std::max<int64_t>(1, nq_pad / 256);
+  const int64_t chunks_max = std::min<int64_t>(sm, (static_cast<int64_t>(sm) * 8 + qt_min - 1) / qt_min + 2);
+  const size_t pre_part = align256(static_cast<size_t>(nq_pad) * chunks_max * kSeedKeep * 4) +
+                          align256(static_cast<size_t>(nq_pad / 64 + 2) * 4);
+  return main_part + pre_part + 256;
 }
 
 int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,

@@ -44,11 +44,16 @@ struct FlatScanParams {
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
   float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
   int64_t dense_ld;
+  int tile_stride;      // base tile visited by step t is t * tile_stride (1 = every tile; > 1 = the strided sample of the pre-pass)
+  const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
+  float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
   int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
 
 // bring-up counters (vdb_debug_read_prof): see include/vdb_cuda.h for the slots
 __device__ unsigned long long g_prof[8];
+
+constexpr int kSeedKeep = 16;   // chunk minima a query keeps per item of the seeding pre-pass
 
 namespace tc {
 constexpr int kThreads = 256;
@@ -69,7 +74,11 @@ constexpr int smem_bytes() {
 }
 }  // namespace tc
 
-template <int kCtaGroup, bool kAResident, int KP, bool kDense = false>
+// kSeed: the seeding pre-pass (flat.cu).  Same pipeline, but the epilogue keeps no candidates: per
+// (query, item) it tracks the kSeedKeep smallest *minima of 32-row chunks* in registers (a branch-free
+// insertion network, so the pass runs at the contraction's speed) and writes them out at the end of
+// the item; the r-th smallest of them over the sample is the query's starting bound for the main pass.
+template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, bool kSeed = false>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -137,8 +146,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_iter) {
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+        if (P.qtile_active != nullptr && __ldg(P.qtile_active + qt) == 0) continue;   // every role skips the same items
         const int t0 = chunk * P.tiles_per_chunk;
         const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
         const int q_row0 = (qt * kCtaGroup + cta_rank) * 128;
@@ -152,7 +162,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           else mbar_arrive_cluster(a_full_bar, 0);
         }
         for (int t = t0; t < t1; ++t, ++tile_iter) {
-          const int b_row0 = t * UMMA_N + cta_rank * 128;
+          const int b_row0 = t * P.tile_stride * UMMA_N + cta_rank * 128;
           for (int kbi = 0; kbi < P.kb; ++kbi) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* st = ring + stage * kStageBytes;
@@ -171,9 +181,10 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           const uint32_t nbuf = tile_iter & 1;
           mbar_wait(norm_empty_bar + nbuf, ((tile_iter >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(norm_full_bar + nbuf, UMMA_N * 4);
-          bulk_load_1d(norm_ring + nbuf * UMMA_N, P.norms + static_cast<int64_t>(t) * UMMA_N, UMMA_N * 4,
+          bulk_load_1d(norm_ring + nbuf * UMMA_N, P.norms + static_cast<int64_t>(t) * P.tile_stride * UMMA_N, UMMA_N * 4,
                        norm_full_bar + nbuf);
         }
+        ++item_iter;
       }
     }
     __syncwarp();
@@ -181,8 +192,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // ===================================== MMA issuer (leader CTA) ==========================
     if (is_leader) {
       int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_iter) {
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int chunk = item / P.n_qtiles;
+        if (P.qtile_active != nullptr && __ldg(P.qtile_active + item % P.n_qtiles) == 0) continue;
         const int t0 = chunk * P.tiles_per_chunk;
         const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
         if (kAResident) { mbar_wait(a_full_bar, item_iter & 1); tc_fence_after(); }
@@ -218,6 +230,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
         if (kAResident && elect_one()) umma_commit<kCtaGroup>(a_empty_bar);
         __syncwarp();
+        ++item_iter;
       }
     }
   } else if (warp >= 4) {
@@ -237,6 +250,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     const long long pf_t0 = clock64();
     for (int item = cluster_id; item < n_items; item += n_clusters) {
       const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
+      if (P.qtile_active != nullptr && __ldg(P.qtile_active + qt) == 0) continue;
       const int t0 = chunk * P.tiles_per_chunk;
       const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
       // Pool lineage: chunks c, c + L, c + 2L, ... of a query tile run in different waves (L * n_qtiles
@@ -251,17 +265,25 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       uint32_t* thr_g = P.thr + q;
       int* handover = P.handover + qt * P.n_pools + slot;   // completed (warp, item) pairs of this lineage
       int cnt = 0;
-      if (gen > 0) {
-        if (lane == 0) wait_counter(handover, gen * 4 * kCtaGroup);
-        __syncwarp();
-        cnt = __ldcg(P.pool_cnt + pool_id);
+      float thr = -CUDART_INF_F;
+      float top[kSeedKeep];
+      if constexpr (kSeed) {
+#pragma unroll
+        for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
+      } else {
+        if (gen > 0) {
+          if (lane == 0) wait_counter(handover, gen * 4 * kCtaGroup);
+          __syncwarp();
+        }
+        // redo pass: the pools of the tile's other queries keep what the main pass left in them
+        if (gen > 0 || P.qtile_active != nullptr) cnt = __ldcg(P.pool_cnt + pool_id);
+        if (live) thr = ld_volatile_thr(thr_g);
       }
-      float thr = live ? ld_volatile_thr(thr_g) : -CUDART_INF_F;
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
-        const uint32_t thr_seen = ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
-        const uint32_t row0 = static_cast<uint32_t>(t) * UMMA_N;
+        const uint32_t thr_seen = kSeed ? 0u : ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
+        const uint32_t row0 = static_cast<uint32_t>(t * P.tile_stride) * UMMA_N;
         const float* nb = norm_ring + buf * UMMA_N;
         long long pf_a = 0, pf_b = 0;
         if (prof) pf_a = clock64();
@@ -298,6 +320,16 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             v[g * 4 + 0] = __float_as_uint(k0); v[g * 4 + 1] = __float_as_uint(k1);
             v[g * 4 + 2] = __float_as_uint(k2); v[g * 4 + 3] = __float_as_uint(k3);
             gm[g] = fminf(fminf(k0, k1), fminf(k2, k3));
+          }
+          if constexpr (kSeed) {
+            float x = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+#pragma unroll
+            for (int i = 0; i < kSeedKeep; ++i) {     // sorted insertion, branch-free
+              const float lo_v = fminf(top[i], x);
+              x = fmaxf(top[i], x);
+              top[i] = lo_v;
+            }
+            return;
           }
           if (kDense) {
             if (live) {
@@ -349,12 +381,18 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
         __syncwarp();                              // all lanes are done with this tile's norms
         if (lane == 0) mbar_arrive(norm_empty_bar + buf);
-        if (live) thr = fminf(thr, ord2f(thr_seen));
+        if (!kSeed && live) thr = fminf(thr, ord2f(thr_seen));
       }
-      __stcg(P.pool_cnt + pool_id, cnt);
-      __threadfence();                             // pool entries + count before the hand-over flag
-      __syncwarp();
-      if (lane == 0) atomicAdd(handover, 1);
+      if constexpr (kSeed) {
+        float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);
+#pragma unroll
+        for (int i = 0; i < kSeedKeep; i += 4) out[i / 4] = make_float4(top[i], top[i + 1], top[i + 2], top[i + 3]);
+      } else {
+        __stcg(P.pool_cnt + pool_id, cnt);
+        __threadfence();                           // pool entries + count before the hand-over flag
+        __syncwarp();
+        if (lane == 0) atomicAdd(handover, 1);
+      }
     }
     if (prof) {
       if (lane == 0) {
