@@ -303,6 +303,24 @@ def run_ours(args) -> int:
         return 0
 
     peaks = _peaks()
+    # live yardstick on this box: cuBLAS TF32 GEMM 8192^3 (best of 10 after 3 warm-ups, CUDA events)
+    cublas_tf32 = None
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((8192, 8192), device=dev)
+        b = torch.randn((8192, 8192), device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(10):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(); torch.matmul(a, b); g1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, g0.elapsed_time(g1))
+        cublas_tf32 = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    except Exception:      # noqa: BLE001 - yardstick only
+        cublas_tf32 = None
     nq_launch = (NQ + world - 1) // world if mode == "queries" else NQ
     flops = 2.0 * nq_launch * (hi - lo) * DIM               # per launch on this rank (2 nq N d)
     pipe_tflops = 3.0 * flops / (scan_ms_mean * 1e-3) / 1e12
@@ -346,8 +364,13 @@ def run_ours(args) -> int:
                      "kernel_ms": scan_ms_mean, "kernel_share_of_step": scan_ms_mean / ms_per_step,
                      "algorithmic_tflops": flops / (scan_ms_mean * 1e-3) / 1e12,
                      "frac_of_burst_peak": pipe_tflops / (peaks["bf16_burst"] / 2.0),
-                     "note": f"achieved = 3 * 2*nq*N*d / t (3xTF32 issues 3 MMAs per product); peak = {peaks['source']} "
-                             "sustained bf16 cuBLAS / 2 (TF32 runs at half the bf16 rate); algorithmic_tflops is the "
+                     "frac_of_nominal_tf32": pipe_tflops / 1125.0,
+                     "cublas_tf32_live_tflops": cublas_tf32,
+                     "note": f"achieved = 3 * 2*nq*N*d / t of the main scan launch (3xTF32 issues 3 MMAs per product; the "
+                             f"seeding pre-pass and the empty redo launch are separate launches inside the step); peak = "
+                             f"{peaks['source']} sustained bf16 cuBLAS / 2 (TF32 runs at half the bf16 rate) - a cuBLAS-derived "
+                             "proxy the kernel can exceed (frac > 1), so the fraction of the nominal dense TF32 rate "
+                             "(1125 TFLOP/s) and a live cuBLAS TF32 8192^3 GEMM are given too; algorithmic_tflops is the "
                              "fp32-equivalent 2*nq*N*d / t"},
         "cpu_baseline": cpu,
         "clocks": clocks,
