@@ -69,7 +69,7 @@ def kernel(path: str) -> None:
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
-    print(f"# Scan kernel, `ncu --set full --clock-control none` ({os.path.basename(path)})\n")
+    print(f"# `ncu --set full --clock-control none` ({os.path.basename(path)})\n")
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         print(f"## `{short(d['Kernel Name'])}` grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
@@ -82,6 +82,11 @@ def kernel(path: str) -> None:
         wr = [float(d[h].replace(",", "")) * (1e9 if units[hdr.index(h)] == "Gbyte" else 1e6 if units[hdr.index(h)] == "Mbyte" else 1)
               for h in hdr if h == "dram__bytes_write.sum"]
         if rd and wr:
+            secs = [float(d[h].replace(",", "")) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(units[hdr.index(h)].replace("second", "s").replace("mss", "ms").replace("uss", "us").replace("nss", "ns"), 1e-3)
+                    for h in hdr if h == "gpu__time_duration.sum"]
+            if secs and secs[0] > 0:
+                print(f"| DRAM read + write per launch / duration | {(rd[0] + wr[0]) / secs[0] / 1e9:.1f} | GB/s |")
+        if rd and wr and "flat_scan_tc" in d["Kernel Name"]:
             with open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json"), "w") as f:
                 json.dump({"kernel": short(d["Kernel Name"]), "dram_bytes_per_launch": rd[0] + wr[0], "source": os.path.basename(path)}, f)
         print()

@@ -64,7 +64,8 @@ ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __re
   float4* qs = reinterpret_cast<float4*>(cnts + W);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = blockIdx.x;
-  for (int j = threadIdx.x; j < d4 * 4; j += W * 32) reinterpret_cast<float*>(qs)[j] = j < d ? qmat[q * ld_q + j] : 0.f;
+  const int d4p = (d4 + 7) & ~7;
+  for (int j = threadIdx.x; j < d4p * 4; j += W * 32) reinterpret_cast<float*>(qs)[j] = j < d ? qmat[q * ld_q + j] : 0.f;
   __syncthreads();
   WarpTopK<KP> sel;
   sel.init(pools + warp * CAP);
@@ -80,17 +81,23 @@ ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __re
       const int id = ids[static_cast<int64_t>(b) * 32 + lane];
       const float4* p = vecs + static_cast<int64_t>(b) * d4 * 32 + lane;
       double acc = 0.0;
-#pragma unroll 4
-      for (int c = 0; c < d4; ++c) {
-        const float4 x = __ldg(p + c * 32);
-        const float4 y = qs[c];
-        if (metric == VDB_METRIC_L2) {
-          // four terms in fp32 (fused multiply-adds), then into the fp64 accumulator: one conversion
-          // per 16 bytes instead of four, relative error of the sum stays ~1e-7
-          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-          acc += static_cast<double>(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
-        } else {
-          acc += static_cast<double>(fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))));
+      // batches of 8 independent 128-bit loads per lane (4 KB of the block in flight per warp); the
+      // tail batch is predicated, the query tile in smem is zero-padded to a multiple of 8
+      for (int c0 = 0; c0 < d4; c0 += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = c0 + u < d4 ? __ldg(p + (c0 + u) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 y = qs[c0 + u];
+          if (metric == VDB_METRIC_L2) {
+            // four terms in fp32 (fused multiply-adds), then into the fp64 accumulator: one conversion
+            // per 16 bytes instead of four, relative error of the sum stays ~1e-7
+            const float d0 = x[u].x - y.x, d1 = x[u].y - y.y, d2 = x[u].z - y.z, d3 = x[u].w - y.w;
+            acc += static_cast<double>(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
+          } else {
+            acc += static_cast<double>(fmaf(x[u].x, y.x, fmaf(x[u].y, y.y, fmaf(x[u].z, y.z, x[u].w * y.w))));
+          }
         }
       }
       const bool valid = id >= 0;
@@ -109,7 +116,7 @@ static int launch_scan(int metric, const float* vecs, const int32_t* ids, const 
                        float pad_value, int64_t id_offset, float* out_d, int64_t* out_i, int64_t* scanned,
                        cudaStream_t stream) {
   const int d4 = (d + 3) / 4;
-  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>(d4) * 16;
+  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>((d4 + 7) & ~7) * 16;
   auto kern = ivf_scan_kernel<KP, W>;
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(

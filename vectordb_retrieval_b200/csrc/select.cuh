@@ -55,6 +55,30 @@ __device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* poo
                                                float* out_d, int64_t* out_i) {
   constexpr int CAP = pool_cap(KP);
   constexpr int E = KP / 32;
+  // The tightest of the warps' bounds is a bound for the whole CTA (that warp alone holds KP keys
+  // below it), so every warp first drops what lies above it from its own pool - in parallel - and
+  // the serial merge below sees little more than KP entries instead of up to W * CAP.
+  __shared__ float thr_s[W];
+  if (lane == 0) thr_s[warp] = mine.thr;
+  __syncthreads();
+  float gthr = thr_s[0];
+#pragma unroll
+  for (int w = 1; w < W; ++w) gthr = fminf(gthr, thr_s[w]);
+  {
+    const uint32_t cut = f2ord(gthr);
+    int kept = 0;
+    for (int base = 0; base < mine.cnt; base += 32) {
+      const int i = base + lane;
+      const uint64_t v = i < mine.cnt ? mine.pool[i] : kEmpty;
+      const bool keep = i < mine.cnt && static_cast<uint32_t>(v >> 32) <= cut;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) mine.pool[kept + __popc(m & ((1u << lane) - 1u))] = v;   // kept <= base: never overtakes the reads
+      kept += __popc(m);
+      __syncwarp();
+    }
+    mine.cnt = kept;
+  }
   if (lane == 0) cnts_smem[warp] = mine.cnt;
   __syncthreads();
   if (warp != 0) return;
