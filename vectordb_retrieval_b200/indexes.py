@@ -100,6 +100,9 @@ class GpuIndexFlat:
         if self._impl is None:
             raise RuntimeError("index is empty")
         with torch.cuda.device(self.home):
+            if hasattr(self._impl, "search_host"):      # replicated base: only this rank's query slice crosses PCIe
+                pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+                return engine.results_to_host(*self._impl.search_host(queries, int(k), 0, pad))
             q = engine.queries_to_device(queries, self.home, self.d)
             return engine.results_to_host(*self.search_device(q, int(k)))
 

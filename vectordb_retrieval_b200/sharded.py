@@ -155,17 +155,47 @@ class ReplicatedFlatIndex:
         nq = q.shape[0]
         if self.world == 1:
             return self.shard.search(q, k, flags, pad_value, impl)
+        lo, hi, per = self._slice(nq)
+        return self._search_slice(q[lo:hi], nq, per, k, flags, pad_value, impl)
+
+    def _slice(self, nq: int) -> Tuple[int, int, int]:
         per = (nq + self.world - 1) // self.world
-        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
-        d_loc = torch.full((per, k), pad_value, dtype=torch.float32, device=q.device)
-        i_loc = torch.full((per, k), -1, dtype=torch.int64, device=q.device)
-        if hi > lo:
-            self.shard.search(q[lo:hi], k, flags, pad_value, impl, out=(d_loc[: hi - lo], i_loc[: hi - lo]))
-        d_all = torch.empty((self.world * per, k), dtype=torch.float32, device=q.device)
-        i_all = torch.empty((self.world * per, k), dtype=torch.int64, device=q.device)
+        return min(nq, self.rank * per), min(nq, (self.rank + 1) * per), per
+
+    def _search_slice(self, q_loc: torch.Tensor, nq: int, per: int, k: int, flags: int, pad_value: float, impl: int):
+        import torch.distributed as dist
+        dev = self.shard.dev
+        d_loc = torch.full((per, k), pad_value, dtype=torch.float32, device=dev)
+        i_loc = torch.full((per, k), -1, dtype=torch.int64, device=dev)
+        if q_loc.shape[0] > 0:
+            self.shard.search(q_loc, k, flags, pad_value, impl, out=(d_loc[: q_loc.shape[0]], i_loc[: q_loc.shape[0]]))
+        d_all = torch.empty((self.world * per, k), dtype=torch.float32, device=dev)
+        i_all = torch.empty((self.world * per, k), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(d_all, d_loc, group=self.group)
         dist.all_gather_into_tensor(i_all, i_loc, group=self.group)
         return d_all[:nq], i_all[:nq]
+
+    def search_host(self, queries, k: int, flags: int = 0, pad_value: Optional[float] = None, impl: int = 0):
+        """Host query batch in, device results out: only this rank's slice of the batch crosses PCIe."""
+        eng = self.engine
+        if self.world == 1 or isinstance(queries, torch.Tensor):
+            return self.search(eng.queries_to_device(queries, self.shard.dev, self.shard.d), k, flags, pad_value, impl)
+        descending = self.metric != "l2" and not (flags & (eng._lib.OUT_NEGATE | eng._lib.OUT_ONE_MINUS))
+        if pad_value is None:
+            pad_value = -eng.FLT_MAX if descending else eng.FLT_MAX
+        import numpy as np
+        qh = np.asarray(queries)
+        if qh.ndim == 1:
+            qh = qh.reshape(1, -1)
+        if qh.ndim != 2 or qh.shape[1] != self.shard.d:
+            raise RuntimeError(f"query batch has shape {qh.shape}, expected [nq, {self.shard.d}]")
+        nq = qh.shape[0]
+        lo, hi, per = self._slice(nq)
+        if hi > lo:
+            q_loc = eng.queries_to_device(qh[lo:hi], self.shard.dev, self.shard.d)
+        else:
+            q_loc = torch.empty((0, self.shard.d), dtype=torch.float32, device=self.shard.dev)
+        return self._search_slice(q_loc, nq, per, k, flags, pad_value, impl)
 
 
 def choose_sharding(n_rows: int, kpad: int, world: int, requested: str = "auto") -> str:
