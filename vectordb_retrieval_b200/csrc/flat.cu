@@ -327,16 +327,29 @@ flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __
         acc[u] = 0.0;
       }
       if (cand[0] == kEmpty) break;              // sorted: nothing valid after the first empty slot
-      for (int j = lane; j < kpad; j += 32) {
-        const float xq = -0.5f * (qh[j] + ql[j]);   // operands hold -2q (exact scaling)
+      // 128-bit loads: one instruction covers 128 floats of a row, so for d <= 128 all eight row
+      // reads of the group (4 rows x {hi, lo}) are in flight at once
+      for (int j = lane * 4; j < kpad; j += 128) {
+        const float4 a4 = *reinterpret_cast<const float4*>(qh + j), b4 = *reinterpret_cast<const float4*>(ql + j);
+        const float xq[4] = {-0.5f * (a4.x + b4.x), -0.5f * (a4.y + b4.y), -0.5f * (a4.z + b4.z),
+                             -0.5f * (a4.w + b4.w)};   // operands hold -2q (exact scaling)
+        float4 h4[4], l4[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float xb = __ldg(xh[u] + j) + __ldg(xl[u] + j);
-          if (metric == VDB_METRIC_L2) {
-            const float df = xb - xq;
-            acc[u] += static_cast<double>(df) * static_cast<double>(df);
-          } else {
-            acc[u] += static_cast<double>(xq) * static_cast<double>(xb);
+          h4[u] = __ldg(reinterpret_cast<const float4*>(xh[u] + j));
+          l4[u] = __ldg(reinterpret_cast<const float4*>(xl[u] + j));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float xb[4] = {h4[u].x + l4[u].x, h4[u].y + l4[u].y, h4[u].z + l4[u].z, h4[u].w + l4[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (metric == VDB_METRIC_L2) {
+              const float df = xb[t] - xq[t];
+              acc[u] += static_cast<double>(df) * static_cast<double>(df);
+            } else {
+              acc[u] += static_cast<double>(xq[t]) * static_cast<double>(xb[t]);
+            }
           }
         }
       }
