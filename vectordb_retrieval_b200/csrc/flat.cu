@@ -127,7 +127,7 @@ static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, in
   const int margin = std::max(4, 128 / r);
   const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
   const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
-  if (s_tiles < 8) return pp;                       // small shard: the sample would not pay for itself
+  if (s_tiles < 4) return pp;                       // small shard (< 64k rows at k' = 128): the sample would not pay for itself
   pp.on = true;
   pp.stride = main_plan.n_tiles / s_tiles;
   pp.plan = make_plan(impl, nq, static_cast<int64_t>(s_tiles) * main_plan.tile_rows, kpad, sm);
