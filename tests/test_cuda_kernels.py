@@ -351,3 +351,17 @@ def test_seeded_bounds_misleading_sample_takes_the_redo_pass(eng):
     ref = oracle.faiss_flat_search(base2, q, k, "l2")
     _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
     assert redo > 0, "expected the misleading sample to force at least one query through the redo pass"
+
+
+def test_seeded_bounds_one_cta_variant_and_streamed_query_tile(eng):
+    """The seeding pre-pass has its own kernel instances: cover cta_group::1 and the streamed query
+    tile (d > 128) as well, against the oracle."""
+    from vectordb_retrieval_b200 import _lib
+    for impl, n, d, nq, k in (("tcgen05_1cta", 70000, 24, 90, 10), ("tcgen05", 40000, 160, 50, 10), ("tcgen05_1cta", 40000, 160, 50, 10)):
+        base, q = _data(n, d, nq, seed=n + d)
+        shard = eng.FlatShard(base, "l2", "cuda")
+        _redo_count()
+        D, I = shard.search(torch.from_numpy(q).cuda(), k, 0, oracle.FLT_MAX, _lib.IMPL_NAMES[impl])
+        torch.cuda.synchronize()
+        assert _redo_count() == 0
+        _check(oracle.faiss_flat_search(base, q, k, "l2"), (D.cpu().numpy(), I.cpu().numpy()))

@@ -441,7 +441,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Descriptors are pure functions of (pointer, rows, kpad): a search encodes twelve of them (three
+// launches x four operands), mostly for the same buffers as the previous call, so the last few are
+// kept per thread.
+struct MapCacheEntry { const float* ptr; int64_t rows; int kpad; CUtensorMap map; };
+static int make_operand_map_uncached(CUtensorMap* map, const float* ptr, int64_t rows, int kpad);
 static int make_operand_map(CUtensorMap* map, const float* ptr, int64_t rows, int kpad) {
+  constexpr int kSlots = 16;
+  thread_local MapCacheEntry cache[kSlots] = {};
+  thread_local int next = 0;
+  for (int i = 0; i < kSlots; ++i) {
+    if (cache[i].ptr == ptr && cache[i].rows == rows && cache[i].kpad == kpad) { *map = cache[i].map; return 0; }
+  }
+  const int rc = make_operand_map_uncached(map, ptr, rows, kpad);
+  if (rc) return rc;
+  cache[next] = MapCacheEntry{ptr, rows, kpad, *map};
+  next = (next + 1) % kSlots;
+  return 0;
+}
+
+static int make_operand_map_uncached(CUtensorMap* map, const float* ptr, int64_t rows, int kpad) {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* sym = nullptr;
