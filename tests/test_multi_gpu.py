@@ -53,6 +53,16 @@ for mode in ("rows", "queries"):              # row shards + merge kernel / repl
     algo.build_index(base)
     d, i = algo.batch_search(queries, 50)
     np.save(os.path.join({out!r}, f"d_{{mode}}{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i_{{mode}}{{rank}}.npy"), i)
+# IVF-Flat with replicated centroids and row-sharded lists: same answer as one GPU holding every list
+from vectordb_retrieval_b200 import engine, sharded
+ivf = sharded.DistributedIVFIndex.from_global(base, 64, "l2", dev, nprobe=8)
+qd = torch.from_numpy(queries).to(dev)
+d, i = ivf.search(qd.clone(), 50)
+np.save(os.path.join({out!r}, f"d_ivf{{rank}}.npy"), d.cpu().numpy()); np.save(os.path.join({out!r}, f"i_ivf{{rank}}.npy"), i.cpu().numpy())
+if rank == 0:
+    one = engine.IVFShard(base, ivf.shard.centroids, "l2", dev)
+    d1, i1 = one.search(qd.clone(), 50, 8, 0, engine.FLT_MAX)
+    np.save(os.path.join({out!r}, "d_ivf_single.npy"), d1.cpu().numpy()); np.save(os.path.join({out!r}, "i_ivf_single.npy"), i1.cpu().numpy())
 dist.destroy_process_group()
 """
 
@@ -79,3 +89,6 @@ def test_distributed_flat_index_nccl(tmp_path):
             assert res["ok"], (mode, r, res)
         np.testing.assert_array_equal(np.load(tmp_path / f"i_{mode}0.npy"), np.load(tmp_path / f"i_{mode}{n - 1}.npy"))
     np.testing.assert_array_equal(np.load(tmp_path / "i_rows0.npy"), np.load(tmp_path / "i_queries0.npy"))
+    for r in range(n):        # sharded IVF == single-GPU IVF with the same centroids, on every rank
+        np.testing.assert_array_equal(np.load(tmp_path / f"i_ivf{r}.npy"), np.load(tmp_path / "i_ivf_single.npy"))
+        np.testing.assert_array_equal(np.load(tmp_path / f"d_ivf{r}.npy"), np.load(tmp_path / "d_ivf_single.npy"))

@@ -198,6 +198,60 @@ class ReplicatedFlatIndex:
         return self._search_slice(q_loc, nq, per, k, flags, pad_value, impl)
 
 
+class DistributedIVFIndex:
+    """IVF-Flat across the GPUs of one box: the centroids are replicated, rank r holds the
+    inverted lists of ITS rows (every list is cut by row range), so the union of the ranks' list scans
+    is the single-GPU scan and the (distance, id) merge returns the same result for any GPU count.
+    Exchange = the same allgather of local top-k lists + ``vdb_merge_topk`` as the flat index.
+    Centroids come from rank 0 (k-means accumulates with float atomics, so two ranks training on the
+    same sample would not agree bit for bit) and are broadcast once."""
+
+    def __init__(self, local_vectors, centroids, metric: str = "l2", device=None, id_offset: int = 0, nprobe: int = 1,
+                 group=None):
+        from . import engine
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = dist_info()
+        self.shard = engine.IVFShard(local_vectors, centroids, metric, device, id_offset=id_offset)
+        self.metric = metric
+        self.nprobe = int(nprobe)
+
+    @classmethod
+    def from_global(cls, vectors, nlist: int, metric: str = "l2", device=None, nprobe: int = 1, group=None, niter: int = 10,
+                    seed: int = 1234) -> "DistributedIVFIndex":
+        import torch.distributed as dist
+        from . import engine
+        rank, world = dist_info()
+        dev = engine._require_cuda(device)
+        d = int(vectors.shape[1])
+        if rank == 0:
+            cent = torch.from_numpy(engine.kmeans_train(vectors, nlist, metric, dev, niter=niter, seed=seed)).to(dev)
+        else:
+            cent = torch.empty((nlist, d), dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(cent, src=0, group=group)
+        plan = ShardPlan(int(vectors.shape[0]), world)
+        lo, hi = plan.start(rank), plan.stop(rank)
+        if hi <= lo:
+            raise RuntimeError(f"rank {rank} of {world} owns no rows of a {vectors.shape[0]}-row base")
+        return cls(vectors[lo:hi], cent, metric, dev, id_offset=lo, nprobe=nprobe, group=group)
+
+    def memory_bytes(self) -> int:
+        return self.shard.memory_bytes()
+
+    def search(self, q: torch.Tensor, k: int, flags: int = 0, pad_value: Optional[float] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        eng = self.engine
+        descending = self.metric != "l2" and not (flags & (eng._lib.OUT_NEGATE | eng._lib.OUT_ONE_MINUS))
+        if pad_value is None:
+            pad_value = -eng.FLT_MAX if descending else eng.FLT_MAX
+        d_loc, i_loc = self.shard.search(q, k, self.nprobe, flags, pad_value)
+        if self.world == 1:
+            return d_loc, i_loc
+        d_all, i_all = allgather_topk(d_loc, i_loc, self.group)
+        return eng.merge_topk(d_all, i_all, descending=descending, pad_value=pad_value)
+
+
 def choose_sharding(n_rows: int, kpad: int, world: int, requested: str = "auto") -> str:
     """'rows' (north-star layout: row shards + top-k allgather + merge) or 'queries' (replicated base).
     auto: replicate while the operand set (2 * n * kpad * 4 bytes) stays under 8 GB per GPU."""
