@@ -50,9 +50,12 @@ def launches(path: str) -> None:
     print(f"# Launch list ({os.path.basename(path)})\n")
     print("`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 3 --warmup 3 "
           "--no-cpu-baseline`; per-launch times are cold-cache and serialised - compare shares, not absolutes.\n")
-    print("| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|")
+    ours = {k: v for k, v in agg.items() if not (k.startswith("torch:") or k.startswith("cuBLAS"))}
+    ours_total = sum(sum(v) for v in ours.values()) or 1.0
+    print("| kernel | launches | mean us | total us | share of all launches | share of the search step |\n|---|---|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        print(f"| `{k}` | {len(v)} | {sum(v) / len(v):,.1f} | {sum(v):,.1f} | {100 * sum(v) / total:.1f} % |")
+        step = f"{100 * sum(v) / ours_total:.1f} %" if k in ours else "- (outside the step)"
+        print(f"| `{k}` | {len(v)} | {sum(v) / len(v):,.1f} | {sum(v):,.1f} | {100 * sum(v) / total:.1f} % | {step} |")
 
 
 KEYS = [
