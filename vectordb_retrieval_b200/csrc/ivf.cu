@@ -52,7 +52,7 @@ __global__ void kmeans_accumulate_kernel(const float* __restrict__ x, int64_t n,
 }
 
 template <int KP, int W>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(W * 32, 1024 / (W * 32))
 ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __restrict__ ids,
                 const int32_t* __restrict__ blk_off, int nlist, int d4, const int64_t* __restrict__ probes, int nprobe,
                 const float* __restrict__ qmat, int64_t ld_q, int d, int k, int flags, float pad_value, int64_t id_offset,

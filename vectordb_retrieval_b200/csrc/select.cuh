@@ -14,22 +14,52 @@ struct WarpTopK {
 
   __device__ __forceinline__ void init(uint64_t* p) { pool = p; cnt = 0; thr = CUDART_INF_F; }
 
-  // one out-of-line copy per kernel; state travels by value so the hot loop keeps it in registers
+  // one out-of-line copy per kernel; state travels by value so the hot loop keeps it in registers.
+  // Selection, not a sort (the pool is unordered anyway): radix-select the KP-th key, keep the KP
+  // smallest (key, row) words in place - ~400 instructions where a 256-element bitonic sort took 2 600
+  // (18 % of the rerank kernel's executed instructions, profiles/rerank_kernel_r1.md).
   static __device__ __noinline__ PoolState compact_impl(uint64_t* pool, int cnt, float thr, int lane) {
     __syncwarp();
-    uint64_t v[E];
+    if (cnt <= KP) return PoolState{thr, cnt};
+    uint32_t hi[E], lo[E];
+    bool live[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = e * 32 + lane;
-      v[e] = i < cnt ? pool[i] : kEmpty;
+      live[e] = i < cnt;
+      const uint64_t w = live[e] ? pool[i] : kEmpty;
+      hi[e] = static_cast<uint32_t>(w >> 32);
+      lo[e] = static_cast<uint32_t>(w);
     }
-    warp_sort<E>(v, lane);
+    const uint32_t kth = warp_select_kth<E>(hi, live, KP);
+    int below = 0, equal = 0;
 #pragma unroll
-    for (int e = 0; e < KP / 32; ++e) pool[e * 32 + lane] = v[e];
-    const uint64_t kth = __shfl_sync(0xffffffffu, v[KP / 32 - 1], 31);
-    if (kth != kEmpty) thr = fminf(thr, packed_key(kth));
+    for (int e = 0; e < E; ++e) {
+      below += (live[e] && hi[e] < kth) ? 1 : 0;
+      equal += (live[e] && hi[e] == kth) ? 1 : 0;
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    equal = __reduce_add_sync(0xffffffffu, equal);
+    uint32_t row_cut = 0xffffffffu;                         // keys equal to the bound: keep the lowest rows
+    if (below + equal > KP) {
+      bool tie[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) tie[e] = live[e] && hi[e] == kth;
+      row_cut = warp_select_kth<E>(lo, tie, KP - below);
+    }
+    __syncwarp();                                           // every slot is in registers before the in-place rewrite
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int off = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool keep = live[e] && (hi[e] < kth || (hi[e] == kth && lo[e] <= row_cut));
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) pool[off + __popc(m & lt_mask)] = (static_cast<uint64_t>(hi[e]) << 32) | lo[e];
+      off += __popc(m);
+    }
+    thr = fminf(thr, ord2f(kth));
     __syncwarp();
-    return PoolState{thr, min(cnt, KP)};
+    return PoolState{thr, off};
   }
   __device__ __forceinline__ void compact(int lane) {
     const PoolState st = compact_impl(pool, cnt, thr, lane);
