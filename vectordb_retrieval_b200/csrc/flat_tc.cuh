@@ -217,10 +217,12 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // 4 x K=8 per 32-wide block: +32 bytes inside the swizzle atom
                 umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC, (kbi | k) != 0);
+              if constexpr (!kSeed) {   // the seeding pre-pass only guesses: plain TF32 keys (1e-3 relative) do
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
+                for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_lo + 2 * k, db_hi + 2 * k, IDESC, 1);
+                for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_lo + 2 * k, db_hi + 2 * k, IDESC, 1);
+              }
               umma_commit<kCtaGroup>(empty_bar + stage);
               if (kbi == P.kb - 1) umma_commit<kCtaGroup>(tmem_full_bar + buf);
             }
