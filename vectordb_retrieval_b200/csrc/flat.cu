@@ -147,10 +147,20 @@ flat_tau_kernel(const float* __restrict__ seed, int n_chunks, int64_t nq, int ra
   const int total = n_chunks * kSeedKeep;
   const float* v = seed + q * total;
   uint64_t best[1] = {kEmpty};
-  for (int base = 0; base < total; base += 32) {
-    const int i = base + lane;
-    uint64_t fresh[1] = {i < total ? pack_key(__ldcg(v + i), static_cast<uint32_t>(i)) : kEmpty};
-    warp_merge_keep<1>(best, fresh, lane);
+  for (int base = 0; base < total; base += 128) {            // four independent loads in flight per lane
+    float x[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = base + t * 32 + lane;
+      x[t] = i < total ? __ldcg(v + i) : CUDART_INF_F;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = base + t * 32 + lane;
+      if (base + t * 32 >= total) break;                        // warp-uniform
+      uint64_t fresh[1] = {i < total ? pack_key(x[t], static_cast<uint32_t>(i)) : kEmpty};
+      warp_merge_keep<1>(best, fresh, lane);
+    }
   }
   const uint64_t w = __shfl_sync(0xffffffffu, best[0], rank - 1);
   if (lane == 0) {
