@@ -6,6 +6,7 @@
 #include <cstdio>
 
 #include "flat_tc.cuh"
+#include "select.cuh"
 
 namespace vdb {
 
@@ -447,6 +448,49 @@ merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i
 }
 
 // --------------------------------------------------------------------------------------------
+// Small bases (a coarse quantiser's centroids, the 10k-20k row sets of the reference's published
+// runs): every lineage would spend its whole life in the loose-bound phase - with 4 096 rows and
+// k' = 32 the pools of a query were compacted ~20 times, 0.5 ms for what is 40 us of contraction.
+// There the nq x n key matrix is small enough to exist: the scan writes it (dense-only epilogue,
+// 128-bit stores) and this kernel selects per query with a warp pool in shared memory, leaving
+// the k' smallest (key, row) words as the query's single pool for the usual finalize step.
+constexpr int64_t kDenseMaxRows = 32768;
+constexpr int64_t kDenseMaxBytes = 192ll << 20;
+
+template <int KP>
+__global__ void __launch_bounds__(128)
+dense_select_kernel(const float* __restrict__ keys, int64_t ld, int64_t n, int64_t nq, uint64_t* __restrict__ pools,
+                    int* __restrict__ pool_cnt) {
+  constexpr int CAP = pool_cap(KP);
+  extern __shared__ __align__(16) uint8_t smem_sel[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (q >= nq) return;
+  WarpTopK<KP> sel;
+  sel.init(reinterpret_cast<uint64_t*>(smem_sel) + warp * CAP);
+  const float* row = keys + q * ld;
+  for (int64_t base = 0; base < n; base += 128) {            // four coalesced 128-byte loads in flight
+    float x[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t i = base + t * 32 + lane;
+      x[t] = i < n ? __ldcs(row + i) : CUDART_INF_F;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t i = base + t * 32 + lane;
+      if (base + t * 32 >= n) break;                            // warp-uniform
+      sel.push(i < n, x[t], static_cast<uint32_t>(i), lane);
+    }
+  }
+  if (sel.cnt > KP) sel.compact(lane);
+  __syncwarp();
+  uint64_t* out = pools + q * CAP;
+  for (int i = lane; i < sel.cnt; i += 32) out[i] = sel.pool[i];
+  if (lane == 0) pool_cnt[q] = sel.cnt;
+}
+
+// --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -594,6 +638,34 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   P.pools = reinterpret_cast<uint64_t*>(w + off_pool);
   P.dense = dense; P.dense_ld = n_pad; P.dbg = g_debug_mode;
   P.tile_stride = 1; P.qtile_active = nullptr; P.seed_out = nullptr;
+  P.dense_only = 0;
+  // small base: dense keys + a selection kernel instead of pools filled from a loose bound
+  const size_t off_dense = align256(need);
+  const size_t dense_bytes = static_cast<size_t>(nq_pad) * n_pad * 4;
+  if (plan.cta_group != 0 && dense == nullptr && !pre.on && (g_debug_mode == 0 || g_debug_mode == 7) &&
+      n_pad <= kDenseMaxRows && static_cast<int64_t>(dense_bytes) <= kDenseMaxBytes && ws_bytes >= off_dense + dense_bytes) {
+    FlatScanParams Dn = P;
+    Dn.dense = reinterpret_cast<float*>(w + off_dense);
+    Dn.dense_only = 1;
+    Dn.n_pools = plan.n_chunks;                      // no lineages: nothing is handed over
+    const bool timed_d = g_timing_on && g_timing_n < kTimingSlots;
+    if (timed_d) VDB_CHECK_CUDA(cudaEventRecord(g_ev0[g_timing_n], stream));
+    const int rcd = run_scan<32>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, plan, Dn, sm, stream);
+    if (rcd) return rcd;
+    if (timed_d) VDB_CHECK_CUDA(cudaEventRecord(g_ev1[g_timing_n++], stream));
+    auto sel = dense_select_kernel<KP>;
+    const size_t sel_smem = static_cast<size_t>(4) * CAP * 8;
+    if (sel_smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+    sel<<<static_cast<unsigned>((nq + 3) / 4), 128, sel_smem, stream>>>(Dn.dense, n_pad, n, nq, P.pools, P.pool_cnt);
+    VDB_CHECK_CUDA(cudaGetLastError());
+    count_launches(2 + (out_d != nullptr ? 1 : 0));
+    if (out_d != nullptr) {
+      flat_finalize_kernel<KP><<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
+          metric, hi, lo, kpad, n, id_offset, q_hi, q_lo, nq, 1, P.pools, P.pool_cnt, k, flags, pad_value, out_d, out_i);
+      VDB_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   int* qtile_active = pre.on ? reinterpret_cast<int*>(w + off_act) : nullptr;
   const int64_t n_cnt = nq_pad * plan.n_pools;
   const int64_t n_hand = static_cast<int64_t>(plan.n_qtiles + 1) * plan.n_pools;
@@ -720,7 +792,9 @@ size_t vdb_flat_topk_workspace_bytes(int64_t nq, int k) {
   const int64_t chunks_max = std::min<int64_t>(sm, (static_cast<int64_t>(sm) * 8 + qt_min - 1) / qt_min + 2);
   const size_t pre_part = align256(static_cast<size_t>(nq_pad) * chunks_max * kSeedKeep * 4) +
                           align256(static_cast<size_t>(nq_pad / 64 + 2) * 4);
-  return main_part + pre_part + 256;
+  // small-base path: the dense key matrix (used only while it fits these caps)
+  const size_t dense_part = static_cast<size_t>(std::min<int64_t>(kDenseMaxBytes, nq_pad * kDenseMaxRows * 4)) + 256;
+  return main_part + pre_part + dense_part + 256;
 }
 
 int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* norms, int64_t n, int d,

@@ -42,8 +42,9 @@ struct FlatScanParams {
   uint64_t* pools;      // [nq_pad][n_pools][pool_cap(KP)]
   int* pool_cnt;        // [nq_pad][n_pools]
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
-  float* dense;         // debug: dense keys [nq_pad][dense_ld] or nullptr
+  float* dense;         // kDense: dense keys [nq_pad][dense_ld] (test hook, and the small-base path of flat.cu) or nullptr
   int64_t dense_ld;
+  int dense_only;       // kDense: write the keys and keep no candidates (the selection runs as a separate kernel)
   int tile_stride;      // base tile visited by step t is t * tile_stride (1 = every tile; > 1 = the strided sample of the pre-pass)
   const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
   float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
@@ -272,7 +273,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       if constexpr (kSeed) {
 #pragma unroll
         for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
-      } else {
+      } else if (!(kDense && P.dense_only)) {
         if (gen > 0) {
           if (lane == 0) wait_counter(handover, gen * 4 * kCtaGroup);
           __syncwarp();
@@ -333,11 +334,13 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             }
             return;
           }
-          if (kDense) {
+          if constexpr (kDense) {
             if (live) {
+              uint4* dst = reinterpret_cast<uint4*>(P.dense + q * P.dense_ld + rbase);   // 128-byte aligned
 #pragma unroll
-              for (int i = 0; i < 32; ++i) P.dense[q * P.dense_ld + rbase + i] = __uint_as_float(v[i]);
+              for (int i = 0; i < 8; ++i) dst[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
+            if (P.dense_only) return;
           }
           // Append path.  The lanes OR their 8-bit masks of 4-column groups that beat the bound (one
           // redux); the warp then tests the bits of that warp-uniform mask and visits only flagged
@@ -389,7 +392,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);
 #pragma unroll
         for (int i = 0; i < kSeedKeep; i += 4) out[i / 4] = make_float4(top[i], top[i + 1], top[i + 2], top[i + 3]);
-      } else {
+      } else if (!(kDense && P.dense_only)) {
         __stcg(P.pool_cnt + pool_id, cnt);
         __threadfence();                           // pool entries + count before the hand-over flag
         __syncwarp();
