@@ -4,9 +4,8 @@ set -x
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_final.log
 tail -3 gpurun_out/pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1c.json 2> gpurun_out/bench_r1c.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1c_ref.json 2> gpurun_out/bench_r1c_ref.err; echo "ref rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_c.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 python scripts/scale_100m.py --steps 3 > gpurun_out/scale_100m_r1c_n1.json 2> gpurun_out/scale_100m_r1c_n1.err; echo "c5 rc=$?"; tail -1 gpurun_out/scale_100m_r1c_n1.json | cut -c1-400
-python -c "import json;d=json.load(open('gpurun_out/bench_r1c.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel_ms'],d['roofline']['frac'],d['clocks'])"
-cat gpurun_out/bench_r1c_ref.json | cut -c1-300
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1d.json 2> gpurun_out/bench_r1d.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1d_ref.json 2> gpurun_out/bench_r1d_ref.err; echo "ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1d.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_d.log 2>&1; echo "ncu launches rc=$?"
+python -c "import json;d=json.load(open('gpurun_out/bench_r1d.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel_ms'],d['roofline']['frac'],d['clocks'])"
+cat gpurun_out/bench_r1d_ref.json | cut -c1-300
