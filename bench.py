@@ -68,7 +68,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "25", "-i", str(self.gpu_index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:      # noqa: BLE001 - no nvidia-smi: report nulls
             self.proc = None
