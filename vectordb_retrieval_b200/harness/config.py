@@ -1,5 +1,6 @@
-"""Flat kwargs experiment configuration with YAML I/O (reference: src/experiments/config.py:5-101).
-Unknown keys are ignored; a dataset-wide ``metric`` becomes each algorithm's default."""
+"""Experiment configuration with YAML I/O, table-driven (reference: src/experiments/config.py:5-101).
+Same keys, defaults and behaviour: unknown keys are ignored, a dataset-wide ``metric`` becomes each
+algorithm's default, ``metric`` is only serialised when set."""
 from __future__ import annotations
 
 import copy
@@ -7,27 +8,32 @@ from typing import Any, Dict
 
 import yaml
 
-_DEFAULT_ALGORITHMS = {"exact": {"type": "ExactSearch", "metric": "l2"}}
+# key -> default, in the order the reference serialises them; mutable defaults are deep-copied per instance
+_FIELDS: Dict[str, Any] = {
+    "dataset": "random",
+    "data_dir": "data",
+    "force_download": False,
+    "dataset_options": {},
+    "n_queries": 1000,
+    "topk": 100,
+    "repeat": 1,                 # parsed, unused - as in the reference
+    "query_batch_size": 0,       # 0 = all queries in one call
+    "algorithms": {"exact": {"type": "ExactSearch", "metric": "l2"}},
+    "seed": 42,
+    "output_prefix": "experiment",
+}
 
 
 class ExperimentConfig:
     def __init__(self, **kwargs: Any) -> None:
-        self.dataset = kwargs.get("dataset", "random")
-        self.data_dir = kwargs.get("data_dir", "data")
-        self.force_download = kwargs.get("force_download", False)
-        self.dataset_options = copy.deepcopy(kwargs.get("dataset_options", {}))
-        self.n_queries = kwargs.get("n_queries", 1000)
-        self.topk = kwargs.get("topk", 100)
-        self.repeat = kwargs.get("repeat", 1)               # parsed, unused - as in the reference
-        self.query_batch_size = kwargs.get("query_batch_size", 0)   # 0 = all queries in one call
-        self.algorithms = copy.deepcopy(kwargs.get("algorithms", _DEFAULT_ALGORITHMS))
+        for key, default in _FIELDS.items():
+            value = kwargs.get(key, default)
+            setattr(self, key, copy.deepcopy(value) if isinstance(value, (dict, list)) else value)
         self.metric = kwargs.get("metric")
         if self.metric is not None:
             for cfg in self.algorithms.values():
                 if isinstance(cfg, dict):
                     cfg.setdefault("metric", self.metric)
-        self.seed = kwargs.get("seed", 42)
-        self.output_prefix = kwargs.get("output_prefix", "experiment")
 
     @classmethod
     def from_yaml(cls, yaml_file: str) -> "ExperimentConfig":
@@ -35,8 +41,7 @@ class ExperimentConfig:
             return cls(**yaml.safe_load(f))
 
     def to_dict(self) -> Dict[str, Any]:
-        out = {k: getattr(self, k) for k in ("dataset", "data_dir", "force_download", "dataset_options", "n_queries", "topk",
-                                             "repeat", "query_batch_size", "algorithms", "seed", "output_prefix")}
+        out = {key: getattr(self, key) for key in _FIELDS}
         if self.metric is not None:
             out["metric"] = self.metric
         return out
