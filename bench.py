@@ -5,9 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of the hot path over one query batch: 10 000 queries against the
-1 000 000 x 128 fp32 base, k = 100 (query operand split, tcgen05 scan with the fused top-k bound,
-exact re-scoring + sort; at N > 1 the base is row-sharded over the ranks and the step also
-contains the NCCL allgather of the local top-k lists and the merge kernel - strong scaling).
+1 000 000 x 128 fp32 base, k = 100 (query operand split, seeding pre-pass over a strided sample,
+tcgen05 main scan with the fused top-k bound, verification + redo launch, exact re-scoring + sort).
+At N > 1 (strong scaling) the default layout replicates the 1 GB base and gives every rank nq / N
+queries, one NCCL allgather concatenates the result blocks; ``--shard rows`` is the north-star layout:
+row shards, NCCL allgather of the local top-k lists, merge kernel.
 
 Printed JSON (rank 0, one line):
   value      QPS with the queries already resident in HBM (device time, CUDA events, max over ranks)
