@@ -195,6 +195,21 @@ int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_id
                       int k, int flags, float pad_value, int64_t id_offset,
                       float* out_d, int64_t* out_i, int64_t* scanned_rows, void* stream);
 
+/* ---- Hamming top-k on the tensor pipe (large bases, nbits <= 256) ----------------------------- */
+/* Same contract as vdb_hamming_topk ((distance, id) order, out_d / out_i [nq,k] pre-filled by the
+ * caller with padding), distances from a bf16 +-1 contraction on the tcgen05 pipeline of the flat
+ * scan.  Operands: vdb_hamming_tc_expand turns packed codes [n, words] into bf16 rows of
+ * vdb_hamming_tc_row_bytes(nbits) bytes for rows_pad >= n rows (rows_pad = vdb_flat_npad(n) for the
+ * base together with norms [rows_pad], vdb_flat_nqpad(nq) and negate = 1 for the queries).  The packed
+ * codes are still needed for the sampled bound.  n > 65536. */
+int vdb_hamming_tc_row_bytes(int nbits);
+int vdb_hamming_tc_expand(const uint32_t* codes, int64_t n, int words, int nbits, int negate, void* out, float* norms,
+                          int64_t rows_pad, void* stream);
+size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n);
+int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
+                        const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                        int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -365,3 +365,26 @@ def test_seeded_bounds_one_cta_variant_and_streamed_query_tile(eng):
         torch.cuda.synchronize()
         assert _redo_count() == 0
         _check(oracle.faiss_flat_search(base, q, k, "l2"), (D.cpu().numpy(), I.cpu().numpy()))
+
+
+@pytest.mark.parametrize("nbits,d,n,nq,k", [(256, 50, 70000, 300, 700), (128, 32, 66000, 260, 64), (200, 24, 90000, 257, 1500)])
+def test_hamming_topk_tensor_pipe_matches_popc_path(eng, nbits, d, n, nq, k):
+    """The bf16 +-1 contraction path must return exactly what the popc path returns: same distances,
+    same ids, (distance, id) order - including queries whose sampled bound is too small (duplicated
+    base rows put far more than k rows at distance 0 for some queries)."""
+    rng = np.random.RandomState(nbits + n)
+    base = rng.randn(n, d).astype(np.float32)
+    base[5000:5000 + 2 * k] = base[17]                     # a big tie group
+    q = rng.randn(nq, d).astype(np.float32)
+    q[3] = base[17]
+    proj = rng.randn(nbits, d).astype(np.float32)
+    shard = eng.HammingShard(base, proj, "cuda")
+    qd = torch.from_numpy(q).cuda()
+    shard.tensor_pipe = False
+    d0, i0 = shard.search(qd.clone(), k)
+    shard.tensor_pipe = True
+    d1, i1 = shard.search(qd.clone(), k)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d0.cpu().numpy(), d1.cpu().numpy())
+    np.testing.assert_array_equal(i0.cpu().numpy(), i1.cpu().numpy())
+    assert (i1.cpu().numpy()[3, : 2 * k + 1] >= 0).all()

@@ -31,6 +31,11 @@ void count_launches(int n);   // every kernel launched by the library is counted
     }                                   \
   } while (0)
 
+// lsh.cu: bound T[q] such that, judging by a 32k-row sample, about 1.25 k rows of the n lie within
+// Hamming distance T[q] (popc kernels; hist_scratch [nq][nbits + 1] ints)
+int hamming_sample_bound(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                         int* hist_scratch, int* T, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // Candidate encoding: one 64-bit word, high half = order-preserving image of the fp32 key,
 // low half = row index inside the shard.  Unsigned compare == (key, row) lexicographic compare,

@@ -534,10 +534,10 @@ static int make_operand_map_uncached(CUtensorMap* map, const float* ptr, int64_t
   return 0;
 }
 
-template <int CG, bool ARES, int KP, bool DENSE, bool SEED = false>
+template <int CG, bool ARES, int KP, bool DENSE, bool SEED = false, int HAM = 0>
 static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mbh, const CUtensorMap& mbl,
                      const FlatScanParams& P, int clusters, cudaStream_t stream) {
-  auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE, SEED>;
+  auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE, SEED, HAM>;
   constexpr int smem = tc::smem_bytes<ARES>();
   static bool configured[64] = {};
   int dev = 0;
@@ -717,6 +717,134 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   return 0;
 }
 
+
+// --------------------------------------------------------------------------------------------
+// Hamming top-k on the tensor pipe (replaces faiss.IndexLSH.search for candidate generation,
+// reference src/algorithms/modular.py:477): codes as bf16 +-1 rows, distances from one kind::f16
+// contraction, selection by counting (distances are small integers):
+//   sample bound T (popc kernels, lsh.cu) -> count keys <= T per (segment, query, bin) -> cut bin t*,
+//   rows taken from it per segment, list offsets -> collect the entries <= t* (segment-major, rows
+//   ascending) -> stable counting sort per query = (distance, id) order.  Queries whose sampled bound
+//   turns out too small are recounted without a bound by a second launch over their query tiles only.
+__global__ void ham_expand_kernel(const uint32_t* __restrict__ codes, int64_t n, int words, int nbits, int kwords,
+                                  int negate, uint4* __restrict__ out, float* __restrict__ norms, int64_t rows_pad) {
+  // thread = (row, 32-bit word): writes 32 bf16 values (64 bytes)
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows_pad * kwords) return;
+  const int64_t row = i / kwords;
+  const int w = static_cast<int>(i % kwords);
+  const uint32_t bits = row < n && w < words ? codes[row * words + w] : 0u;
+  const uint32_t one = negate ? 0xBF80u : 0x3F80u, minus = negate ? 0x3F80u : 0xBF80u;   // bf16 +1.0 / -1.0
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = w * 32 + 2 * j + h;
+      v[h] = row < n && b < nbits ? (((bits >> (2 * j + h)) & 1u) ? one : minus) : 0u;
+    }
+    pk[j] = v[0] | (v[1] << 16);
+  }
+  uint4* dst = out + i * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  if (norms != nullptr && w == 0) norms[row] = row < n ? 0.f : CUDART_INF_F;
+}
+
+// after the bounded count: queries with fewer than `need` rows inside their bound are recounted
+__global__ void ham_cut1_kernel(int* __restrict__ hist, int segs, int64_t nq, int nbits, int need, const int* __restrict__ T,
+                                int* __restrict__ bound2, int* __restrict__ qtile_active, int tile_rows) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int bins = nbits + 1;
+  const int t = T[q];
+  long long total = 0;
+  for (int s = 0; s < segs; ++s)
+    for (int b = 0; b <= t; ++b) total += hist[(static_cast<int64_t>(s) * nq + q) * bins + b];
+  if (total < need && t < nbits) {
+    for (int s = 0; s < segs; ++s)
+      for (int b = 0; b < bins; ++b) hist[(static_cast<int64_t>(s) * nq + q) * bins + b] = 0;
+    bound2[q] = nbits;
+    qtile_active[q / tile_rows] = 1;
+  } else {
+    bound2[q] = -1;
+  }
+}
+
+// cut bin, per-segment tie budget and list offsets (segment-major) for every query
+__global__ void ham_cut2_kernel(const int* __restrict__ hist, int segs, int64_t nq, int nbits, int k, const int* __restrict__ T,
+                                const int* __restrict__ bound2, int* __restrict__ cut, int* __restrict__ take,
+                                int* __restrict__ base, int* __restrict__ total_out) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int bins = nbits + 1;
+  const int bound = bound2[q] >= 0 ? bound2[q] : T[q];
+  long long cum = 0;
+  int t = bound, need = 1 << 30;                       // fewer than k rows inside the bound: take them all
+  for (int b = 0; b <= bound; ++b) {
+    long long c = 0;
+    for (int s = 0; s < segs; ++s) c += hist[(static_cast<int64_t>(s) * nq + q) * bins + b];
+    if (cum + c >= k) { t = b; need = static_cast<int>(k - cum); break; }
+    cum += c;
+  }
+  int run = 0;
+  for (int s = 0; s < segs; ++s) {
+    const int* h = hist + (static_cast<int64_t>(s) * nq + q) * bins;
+    int below = 0;
+    for (int b = 0; b < t; ++b) below += h[b];
+    const int tk = min(need, h[t]);
+    need -= tk;
+    take[static_cast<int64_t>(s) * nq + q] = tk;
+    base[static_cast<int64_t>(s) * nq + q] = run;
+    run += below + tk;
+  }
+  cut[q] = t;
+  total_out[q] = min(run, k);
+}
+
+// stable counting sort of a query's collected (distance, row) words -> (distance, id) order
+__global__ void __launch_bounds__(128)
+ham_place_kernel(const uint64_t* __restrict__ list, const int* __restrict__ total, int64_t nq, int nbits, int k,
+                 int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  extern __shared__ int cur_all[];                     // [4][nbits + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  if (q >= nq) return;
+  const int bins = nbits + 1;
+  int* cur = cur_all + warp * bins;
+  for (int b = lane; b < bins; b += 32) cur[b] = 0;
+  __syncwarp();
+  const int n_e = total[q];
+  const uint64_t* src = list + q * k;
+  for (int i = lane; i < n_e; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 32), 1);
+  __syncwarp();
+  if (lane == 0) {
+    int run = 0;
+    for (int b = 0; b < bins; ++b) { const int c = cur[b]; cur[b] = run; run += c; }
+  }
+  __syncwarp();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int base = 0; base < n_e; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < n_e;
+    const uint64_t w = valid ? src[i] : 0ull;
+    const int dist = valid ? static_cast<int>(w >> 32) : -1 - lane;      // invalid lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, dist);
+    const int rank = __popc(peers & lt_mask);
+    if (valid) {
+      const int slot = cur[dist] + rank;
+      out_d[q * k + slot] = static_cast<float>(dist);
+      out_i[q * k + slot] = static_cast<int64_t>(static_cast<uint32_t>(w)) + id_offset;
+    }
+    __syncwarp();
+    if (valid && rank == 0) cur[dist] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+
+
 }  // namespace vdb
 
 using namespace vdb;
@@ -852,6 +980,91 @@ int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t 
     default: merge_topk_kernel<512><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
   }
   count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vdb_hamming_tc_row_bytes(int nbits) { return nbits <= 0 || nbits > 256 ? 0 : (nbits + 63) / 64 * 128; }
+
+int vdb_hamming_tc_expand(const uint32_t* codes, int64_t n, int words, int nbits, int negate, void* out, float* norms,
+                          int64_t rows_pad, void* stream) {
+  const int rb = vdb_hamming_tc_row_bytes(nbits);
+  VDB_REQUIRE(rb != 0 && n > 0 && rows_pad >= n && words >= (nbits + 31) / 32, "vdb_hamming_tc_expand: bad shape (nbits <= 256)");
+  const int kwords = rb / 64;
+  const int64_t threads = rows_pad * kwords;
+  ham_expand_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      codes, n, words, nbits, kwords, negate, static_cast<uint4*>(out), norms, rows_pad);
+  count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n) {
+  const int rb = vdb_hamming_tc_row_bytes(nbits);
+  if (nq <= 0 || rb == 0 || k < 1 || n <= 0) return 0;
+  int sm = 148;
+  vdb_sm_count(&sm);
+  const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, vdb_flat_npad(n), rb / 4, sm);
+  const int64_t segs = plan.n_chunks, bins = nbits + 1;
+  return align256(static_cast<size_t>(segs) * nq * bins * 4) + 4 * align256(static_cast<size_t>(nq) * 4) +
+         2 * align256(static_cast<size_t>(segs) * nq * 4) + align256(static_cast<size_t>(plan.n_qtiles + 1) * 4) +
+         align256(static_cast<size_t>(nq) * k * 8) + 256;
+}
+
+int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
+                        const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                        int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
+  const int rb = vdb_hamming_tc_row_bytes(nbits);
+  VDB_REQUIRE(rb != 0 && n > 65536 && nq > 0 && k >= 1 && n < (int64_t(1) << 32), "vdb_hamming_topk_tc: bad shape (nbits <= 256, n > 65536)");
+  VDB_REQUIRE(workspace != nullptr && workspace_bytes >= vdb_hamming_tc_workspace_bytes(nq, nbits, k, n),
+              "vdb_hamming_topk_tc: workspace too small");
+  int sm = 0;
+  if (vdb_sm_count(&sm)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int kpad = rb / 4;                                     // the code rows seen as fp32 rows: same bytes, same tiles
+  const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
+  const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, n_pad, kpad, sm);
+  const int segs = plan.n_chunks, bins = nbits + 1;
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  size_t off = 0;
+  int* hist = reinterpret_cast<int*>(w + off);   off += align256(static_cast<size_t>(segs) * nq * bins * 4);
+  int* T = reinterpret_cast<int*>(w + off);      off += align256(static_cast<size_t>(nq) * 4);
+  int* bound2 = reinterpret_cast<int*>(w + off); off += align256(static_cast<size_t>(nq) * 4);
+  int* cut = reinterpret_cast<int*>(w + off);    off += align256(static_cast<size_t>(nq) * 4);
+  int* total = reinterpret_cast<int*>(w + off);  off += align256(static_cast<size_t>(nq) * 4);
+  int* take = reinterpret_cast<int*>(w + off);   off += align256(static_cast<size_t>(segs) * nq * 4);
+  int* lbase = reinterpret_cast<int*>(w + off);  off += align256(static_cast<size_t>(segs) * nq * 4);
+  int* active = reinterpret_cast<int*>(w + off); off += align256(static_cast<size_t>(plan.n_qtiles + 1) * 4);
+  uint64_t* list = reinterpret_cast<uint64_t*>(w + off);
+
+  if (hamming_sample_bound(codes, n, qcodes, nq, nbits, k, hist, T, s)) return 3;      // hist doubles as its scratch
+  VDB_CHECK_CUDA(cudaMemsetAsync(hist, 0, static_cast<size_t>(segs) * nq * bins * 4, s));
+  VDB_CHECK_CUDA(cudaMemsetAsync(active, 0, static_cast<size_t>(plan.n_qtiles + 1) * 4, s));
+
+  FlatScanParams P{};
+  P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
+  P.n_chunks = plan.n_chunks; P.n_pools = plan.n_chunks; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.tile_stride = 1; P.ham_nbits = nbits; P.ham_hist = hist; P.ham_k = k;
+  const float* bq = static_cast<const float*>(q_bf16);
+  const float* bb = static_cast<const float*>(base_bf16);
+  CUtensorMap mq, mb;
+  if (make_operand_map(&mq, bq, nq_pad, kpad) || make_operand_map(&mb, bb, n_pad, kpad)) return 3;
+  const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
+
+  P.ham_bound = T;
+  if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+  ham_cut1_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, static_cast<int>(std::min<int64_t>(k, n)), T, bound2, active,
+                                          plan.tile_rows);
+  FlatScanParams R = P;
+  R.ham_bound = bound2; R.qtile_active = active;
+  if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, R, plan.clusters, s)) return 3;
+  ham_cut2_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, T, bound2, cut, take, lbase, total);
+  FlatScanParams C = P;
+  C.ham_bound = cut; C.ham_take = take; C.ham_base = lbase; C.ham_list = list;
+  if (launch_tc<2, true, 32, false, false, 2>(mq, mq, mb, mb, C, plan.clusters, s)) return 3;
+  ham_place_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, static_cast<size_t>(4) * bins * sizeof(int), s>>>(
+      list, total, nq, nbits, k, id_offset, out_d, out_i);
+  count_launches(6);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -48,6 +48,15 @@ struct FlatScanParams {
   int tile_stride;      // base tile visited by step t is t * tile_stride (1 = every tile; > 1 = the strided sample of the pre-pass)
   const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
   float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
+  // Hamming scan (kHam, lsh.cu): operands are bf16 +-1 codes (queries negated, so key = -dot and
+  // ham = (nbits + key) / 2); 1 = count keys <= the per-query bound into hist, 2 = collect keys <= the cut
+  int ham_nbits;
+  const int* ham_bound; // [nq]  mode 1: bound T (-1 = query off); mode 2: cut bin t (-1 = off)
+  int* ham_hist;        // mode 1: [n_chunks][nq][nbits + 1]
+  const int* ham_take;  // mode 2: [n_chunks][nq] ties of bin t this segment keeps (the first ones in row order)
+  const int* ham_base;  // mode 2: [n_chunks][nq] slot of the segment's first entry in the query's list
+  uint64_t* ham_list;   // mode 2: [nq][ham_k] (distance << 32 | row), segment-major
+  int ham_k;
   int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
 
@@ -79,7 +88,7 @@ constexpr int smem_bytes() {
 // (query, item) it tracks the kSeedKeep smallest *minima of 32-row chunks* in registers (a branch-free
 // insertion network, so the pass runs at the contraction's speed) and writes them out at the end of
 // the item; the r-th smallest of them over the sample is the query's starting bound for the main pass.
-template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, bool kSeed = false>
+template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, bool kSeed = false, int kHam = 0>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -91,6 +100,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   constexpr int TMEM_COLS = 2 * UMMA_N;       // double-buffered accumulator
   constexpr int CAP = pool_cap(KP);
   constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
+  constexpr uint32_t IDESC_BF16 = make_idesc_bf16(UMMA_M, UMMA_N);
+  static_assert(kHam == 0 || (kAResident && !kDense && !kSeed), "the Hamming scan uses the resident query tile");
+  constexpr int kOps = kHam != 0 ? 1 : 2;      // operand arrays in use: hi only / hi and lo
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -157,9 +169,10 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           if (item_iter > 0) mbar_wait(a_empty_bar, (item_iter - 1) & 1);
           for (int kbi = 0; kbi < P.kb; ++kbi) {
             tma_load_2d<kCtaGroup>(a_res + kbi * tc::kBlockBytes, &map_q_hi, a_full_bar, kbi * 32, q_row0);
-            tma_load_2d<kCtaGroup>(a_res + (tc::kMaxResidentKb + kbi) * tc::kBlockBytes, &map_q_lo, a_full_bar, kbi * 32, q_row0);
+            if (kOps == 2)
+              tma_load_2d<kCtaGroup>(a_res + (tc::kMaxResidentKb + kbi) * tc::kBlockBytes, &map_q_lo, a_full_bar, kbi * 32, q_row0);
           }
-          if (is_leader) mbar_arrive_expect_tx(a_full_bar, kCtaGroup * P.kb * 2 * tc::kBlockBytes);
+          if (is_leader) mbar_arrive_expect_tx(a_full_bar, kCtaGroup * P.kb * kOps * tc::kBlockBytes);
           else mbar_arrive_cluster(a_full_bar, 0);
         }
         for (int t = t0; t < t1; ++t, ++tile_iter) {
@@ -172,8 +185,8 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
               tma_load_2d<kCtaGroup>(st + 3 * tc::kBlockBytes, &map_q_lo, full_bar + stage, kbi * 32, q_row0);
             }
             tma_load_2d<kCtaGroup>(st, &map_b_hi, full_bar + stage, kbi * 32, b_row0);
-            tma_load_2d<kCtaGroup>(st + tc::kBlockBytes, &map_b_lo, full_bar + stage, kbi * 32, b_row0);
-            if (is_leader) mbar_arrive_expect_tx(full_bar + stage, kCtaGroup * kStageBytes);
+            if (kOps == 2) tma_load_2d<kCtaGroup>(st + tc::kBlockBytes, &map_b_lo, full_bar + stage, kbi * 32, b_row0);
+            if (is_leader) mbar_arrive_expect_tx(full_bar + stage, kCtaGroup * (kOps == 2 ? kStageBytes : tc::kBlockBytes));
             else mbar_arrive_cluster(full_bar + stage, 0);
             if (++stage == tc::kStages) { stage = 0; phase ^= 1; }
           }
@@ -215,10 +228,15 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                                                : smem_u32(st + 3 * tc::kBlockBytes);
               const uint64_t da_hi = make_sw128_kmajor_desc(a_hi), da_lo = make_sw128_kmajor_desc(a_lo);
               const uint64_t db_hi = make_sw128_kmajor_desc(b_hi), db_lo = make_sw128_kmajor_desc(b_lo);
+              if constexpr (kHam != 0) {   // bf16 codes: 64 elements per 128-byte block, K = 16 per MMA
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC_BF16, (kbi | k) != 0);
+              } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // 4 x K=8 per 32-wide block: +32 bytes inside the swizzle atom
                 umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC, (kbi | k) != 0);
-              if constexpr (!kSeed) {   // the seeding pre-pass only guesses: plain TF32 keys (1e-3 relative) do
+              }
+              if constexpr (!kSeed && kHam == 0) {   // the seeding pre-pass only guesses: plain TF32 keys (1e-3 relative) do
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
 #pragma unroll
@@ -270,7 +288,20 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       int cnt = 0;
       float thr = -CUDART_INF_F;
       float top[kSeedKeep];
-      if constexpr (kSeed) {
+      int ham_t = -1, ham_take = 0, ham_seen = 0;
+      int* ham_hist = nullptr;
+      uint64_t* ham_out = nullptr;
+      if constexpr (kHam != 0) {
+        // keys are -dot (integers): ham <= b  <=>  key <= 2b - nbits; the filter compares with `<`
+        if (live) ham_t = P.ham_bound[q];
+        if (ham_t >= 0) thr = static_cast<float>(2 * ham_t - P.ham_nbits) + 0.5f;
+        if (kHam == 1) {
+          ham_hist = P.ham_hist + (static_cast<int64_t>(chunk) * P.nq + q) * (P.ham_nbits + 1);
+        } else if (ham_t >= 0) {
+          ham_take = P.ham_take[static_cast<int64_t>(chunk) * P.nq + q];
+          ham_out = P.ham_list + q * P.ham_k + P.ham_base[static_cast<int64_t>(chunk) * P.nq + q];
+        }
+      } else if constexpr (kSeed) {
 #pragma unroll
         for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
       } else if (!(kDense && P.dense_only)) {
@@ -285,7 +316,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       for (int t = t0; t < t1; ++t, ++tile_iter) {
         const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
-        const uint32_t thr_seen = kSeed ? 0u : ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
+        const uint32_t thr_seen = (kSeed || kHam != 0) ? 0u : ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
         const uint32_t row0 = static_cast<uint32_t>(t * P.tile_stride) * UMMA_N;
         const float* nb = norm_ring + buf * UMMA_N;
         long long pf_a = 0, pf_b = 0;
@@ -352,6 +383,33 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 #pragma unroll
           for (int g = 0; g < 8; ++g) gmask |= gm[g] < thr ? (1u << g) : 0u;
           const unsigned um = __reduce_or_sync(0xffffffffu, gmask);
+          if constexpr (kHam != 0) {
+            if (um != 0u) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (um & (1u << g)) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float key = __uint_as_float(v[g * 4 + u]);
+                    if (key < thr) {                                   // ham <= bound (padding rows carry +inf)
+                      const int ham = (P.ham_nbits + static_cast<int>(key)) >> 1;
+                      if (kHam == 1) {
+                        atomicAdd(ham_hist + ham, 1);
+                      } else {
+                        const bool tie = ham == ham_t;
+                        if (!tie || ham_seen < ham_take) {
+                          ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
+                          ++cnt;
+                        }
+                        ham_seen += tie ? 1 : 0;
+                      }
+                    }
+                  }
+                }
+              }
+            }
+            return;
+          }
           if (um != 0u && P.dbg != 2) {
             long long th0 = 0;
             if (prof) { th0 = clock64(); pf_hits += 1; }
@@ -386,13 +444,13 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
         __syncwarp();                              // all lanes are done with this tile's norms
         if (lane == 0) mbar_arrive(norm_empty_bar + buf);
-        if (!kSeed && live) thr = fminf(thr, ord2f(thr_seen));
+        if (!kSeed && kHam == 0 && live) thr = fminf(thr, ord2f(thr_seen));
       }
       if constexpr (kSeed) {
         float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);
 #pragma unroll
         for (int i = 0; i < kSeedKeep; i += 4) out[i / 4] = make_float4(top[i], top[i + 1], top[i + 2], top[i + 3]);
-      } else if (!(kDense && P.dense_only)) {
+      } else if (kHam == 0 && !(kDense && P.dense_only)) {
         __stcg(P.pool_cnt + pool_id, cnt);
         __threadfence();                           // pool entries + count before the hand-over flag
         __syncwarp();

@@ -314,6 +314,34 @@ static int run_hamming(const uint32_t* codes, int64_t n, const uint32_t* qcodes,
   return 0;
 }
 
+template <int W4>
+static int sample_bound_impl(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                             int* hist, int* T, cudaStream_t s) {
+  constexpr int QT = queries_per_warp<W4>();
+  constexpr int64_t kSample = 32768;
+  const int bins = nbits + 1;
+  const unsigned blocks = static_cast<unsigned>((nq + 4 * QT - 1) / (4 * QT));
+  const size_t smem = static_cast<size_t>(4) * QT * bins * sizeof(int);
+  auto count = hamming_count_kernel<W4>;
+  if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t rows = std::min<int64_t>(n, kSample);
+  count<<<dim3(blocks, 1), 128, smem, s>>>(reinterpret_cast<const uint4*>(codes), 0, rows, rows,
+                                           reinterpret_cast<const uint4*>(qcodes), nq, nbits, nullptr, nullptr, hist);
+  hamming_bound_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(hist, nq, nbits, rows, n, k, T);
+  count_launches(2);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int hamming_sample_bound(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                         int* hist_scratch, int* T, cudaStream_t stream) {
+  switch (vdb_lsh_code_words(nbits) / 4) {
+    case 1: return sample_bound_impl<1>(codes, n, qcodes, nq, nbits, k, hist_scratch, T, stream);
+    case 2: return sample_bound_impl<2>(codes, n, qcodes, nq, nbits, k, hist_scratch, T, stream);
+    default: set_error("hamming_sample_bound: nbits %d not supported", nbits); return 2;
+  }
+}
+
 }  // namespace vdb
 
 using namespace vdb;
