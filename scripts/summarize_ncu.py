@@ -23,7 +23,11 @@ def short(name: str) -> str:
         return "cuBLAS TF32 GEMM 8192^3 (bench.py's live yardstick, outside the timed region)"
     if "flat_scan_tc_kernel<" in name:     # the template arguments tell the seeding pre-pass (..., 32, 0, 1) from the main scan
         args = name.split("flat_scan_tc_kernel<")[1].split(">")[0].replace("(int)", "").replace("(bool)", "").replace(" ", "")
-        return "flat_scan_tc_kernel<" + args + ">" + (" (seeding pre-pass)" if args.endswith(",1") else " (main scan)")
+        parts = args.split(",")
+        seed = len(parts) >= 5 and parts[4] == "1"
+        ham = parts[5] if len(parts) >= 6 else "0"
+        kind = " (seeding pre-pass)" if seed else {"1": " (Hamming count)", "2": " (Hamming collect)"}.get(ham, " (main scan)")
+        return "flat_scan_tc_kernel<" + args + ">" + kind
     for cut in ("<", "("):
         if cut in name:
             name = name.split(cut)[0]

@@ -36,6 +36,11 @@ void count_launches(int n);   // every kernel launched by the library is counted
 int hamming_sample_bound(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
                          int* hist_scratch, int* T, cudaStream_t stream);
 
+// lsh.cu: the exact popc path (count every distance, cut, emit) for the queries flagged in `only`;
+// ws as for vdb_hamming_topk
+int hamming_topk_subset(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                        int64_t id_offset, float* out_d, int64_t* out_i, void* ws, const uint8_t* only, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // Candidate encoding: one 64-bit word, high half = order-preserving image of the fp32 key,
 // low half = row index inside the shard.  Unsigned compare == (key, row) lexicographic compare,

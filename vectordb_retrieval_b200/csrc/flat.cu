@@ -752,98 +752,83 @@ __global__ void ham_expand_kernel(const uint32_t* __restrict__ codes, int64_t n,
   if (norms != nullptr && w == 0) norms[row] = row < n ? 0.f : CUDART_INF_F;
 }
 
-// after the bounded count: queries with fewer than `need` rows inside their bound are recounted
-__global__ void ham_cut1_kernel(int* __restrict__ hist, int segs, int64_t nq, int nbits, int need, const int* __restrict__ T,
-                                int* __restrict__ bound2, int* __restrict__ qtile_active, int tile_rows) {
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  const int bins = nbits + 1;
-  const int t = T[q];
-  long long total = 0;
-  for (int s = 0; s < segs; ++s)
-    for (int b = 0; b <= t; ++b) total += hist[(static_cast<int64_t>(s) * nq + q) * bins + b];
-  if (total < need && t < nbits) {
-    for (int s = 0; s < segs; ++s)
-      for (int b = 0; b < bins; ++b) hist[(static_cast<int64_t>(s) * nq + q) * bins + b] = 0;
-    bound2[q] = nbits;
-    qtile_active[q / tile_rows] = 1;
-  } else {
-    bound2[q] = -1;
-  }
-}
-
-// cut bin, per-segment tie budget and list offsets (segment-major) for every query
-__global__ void ham_cut2_kernel(const int* __restrict__ hist, int segs, int64_t nq, int nbits, int k, const int* __restrict__ T,
-                                const int* __restrict__ bound2, int* __restrict__ cut, int* __restrict__ take,
-                                int* __restrict__ base, int* __restrict__ total_out) {
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  const int bins = nbits + 1;
-  const int bound = bound2[q] >= 0 ? bound2[q] : T[q];
-  long long cum = 0;
-  int t = bound, need = 1 << 30;                       // fewer than k rows inside the bound: take them all
-  for (int b = 0; b <= bound; ++b) {
-    long long c = 0;
-    for (int s = 0; s < segs; ++s) c += hist[(static_cast<int64_t>(s) * nq + q) * bins + b];
-    if (cum + c >= k) { t = b; need = static_cast<int>(k - cum); break; }
-    cum += c;
-  }
-  int run = 0;
-  for (int s = 0; s < segs; ++s) {
-    const int* h = hist + (static_cast<int64_t>(s) * nq + q) * bins;
-    int below = 0;
-    for (int b = 0; b < t; ++b) below += h[b];
-    const int tk = min(need, h[t]);
-    need -= tk;
-    take[static_cast<int64_t>(s) * nq + q] = tk;
-    base[static_cast<int64_t>(s) * nq + q] = run;
-    run += below + tk;
-  }
-  cut[q] = t;
-  total_out[q] = min(run, k);
-}
-
-// stable counting sort of a query's collected (distance, row) words -> (distance, id) order
+// Selection over what the scan collected for a query (lists per segment, rows ascending, every key
+// within the sampled bound): histogram of the distances in shared memory, cut bin and tie budget, then
+// a stable placement pass - segments and rows arrive ascending, so equal distances keep id order.
+// A query whose lists overflowed or hold fewer than `need` entries is flagged for the exact popc path.
 __global__ void __launch_bounds__(128)
-ham_place_kernel(const uint64_t* __restrict__ list, const int* __restrict__ total, int64_t nq, int nbits, int k,
-                 int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  extern __shared__ int cur_all[];                     // [4][nbits + 1]
+ham_select_kernel(const uint64_t* __restrict__ list, const int* __restrict__ lcnt, int segs, int cap, int64_t nq, int nbits,
+                  int k, int need, int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i,
+                  uint8_t* __restrict__ fallback) {
+  extern __shared__ int cur_all[];                     // [4][nbits + 2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
   if (q >= nq) return;
   const int bins = nbits + 1;
-  int* cur = cur_all + warp * bins;
-  for (int b = lane; b < bins; b += 32) cur[b] = 0;
+  int* cur = cur_all + warp * (bins + 1);
+  for (int b = lane; b <= bins; b += 32) cur[b] = 0;
   __syncwarp();
-  const int n_e = total[q];
-  const uint64_t* src = list + q * k;
-  for (int i = lane; i < n_e; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 32), 1);
-  __syncwarp();
-  if (lane == 0) {
-    int run = 0;
-    for (int b = 0; b < bins; ++b) { const int c = cur[b]; cur[b] = run; run += c; }
+  long long total = 0;
+  bool over = false;
+  for (int s = 0; s < segs; ++s) {
+    const int c = lcnt[static_cast<int64_t>(s) * nq + q];
+    over |= c > cap;
+    total += c;
   }
+  if (over || total < need) {
+    if (lane == 0) fallback[q] = 1;
+    return;
+  }
+  if (lane == 0) fallback[q] = 0;
+  for (int s = 0; s < segs; ++s) {
+    const int c = lcnt[static_cast<int64_t>(s) * nq + q];
+    const uint64_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
+    for (int i = lane; i < c; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 32), 1);
+  }
+  __syncwarp();
+  int t = bins, tie_budget = 0;
+  if (lane == 0) {                                     // bins -> output offsets; cut bin and its budget
+    int run = 0;
+    t = nbits; tie_budget = 1 << 30;
+    bool found = false;
+    for (int b = 0; b < bins; ++b) {
+      const int c = cur[b];
+      if (!found && run + c >= k) { t = b; tie_budget = k - run; found = true; }
+      cur[b] = run;
+      run += c;
+    }
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  tie_budget = __shfl_sync(0xffffffffu, tie_budget, 0);
   __syncwarp();
   const unsigned lt_mask = (1u << lane) - 1u;
-  for (int base = 0; base < n_e; base += 32) {
-    const int i = base + lane;
-    const bool valid = i < n_e;
-    const uint64_t w = valid ? src[i] : 0ull;
-    const int dist = valid ? static_cast<int>(w >> 32) : -1 - lane;      // invalid lanes match nobody
-    const unsigned peers = __match_any_sync(0xffffffffu, dist);
-    const int rank = __popc(peers & lt_mask);
-    if (valid) {
-      const int slot = cur[dist] + rank;
-      out_d[q * k + slot] = static_cast<float>(dist);
-      out_i[q * k + slot] = static_cast<int64_t>(static_cast<uint32_t>(w)) + id_offset;
+  int seen = 0;                                        // ties of the cut bin met so far (warp-uniform)
+  for (int s = 0; s < segs; ++s) {
+    const int c = lcnt[static_cast<int64_t>(s) * nq + q];
+    const uint64_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
+    for (int base = 0; base < c; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < c;
+      const uint64_t w = valid ? src[i] : 0ull;
+      const int dist = valid ? static_cast<int>(w >> 32) : -1;
+      const bool tie = valid && dist == t;
+      const unsigned tie_m = __ballot_sync(0xffffffffu, tie);
+      const bool takes = valid && (dist < t || (tie && seen + __popc(tie_m & lt_mask) < tie_budget));
+      seen += __popc(tie_m);
+      const unsigned peers = __match_any_sync(0xffffffffu, takes ? dist : -2 - lane);
+      if (takes) {
+        const int slot = cur[dist] + __popc(peers & lt_mask);
+        if (slot < k) {
+          out_d[q * k + slot] = static_cast<float>(dist);
+          out_i[q * k + slot] = static_cast<int64_t>(static_cast<uint32_t>(w)) + id_offset;
+        }
+      }
+      __syncwarp();
+      if (takes && (peers & lt_mask) == 0u) cur[dist] += __popc(peers);
+      __syncwarp();
     }
-    __syncwarp();
-    if (valid && rank == 0) cur[dist] += __popc(peers);
-    __syncwarp();
   }
 }
-
-
 
 }  // namespace vdb
 
@@ -999,16 +984,25 @@ int vdb_hamming_tc_expand(const uint32_t* codes, int64_t n, int words, int nbits
   return 0;
 }
 
+static int ham_list_cap(int64_t n, int k, int segs) {
+  // expected entries per (segment, query): the sampled bound aims at lam + 4 sqrt(lam) + 4 of 32 768 sample
+  // rows, and rounds up to a whole distance bin; four times the per-segment average, plus slack
+  const double s = 32768.0, lam = static_cast<double>(k) * s / static_cast<double>(n);
+  const double target = (lam + 4.0 * sqrt(lam) + 4.0) * static_cast<double>(n) / s;
+  return static_cast<int>(4.0 * target / segs) + 128;
+}
+
 size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n) {
   const int rb = vdb_hamming_tc_row_bytes(nbits);
   if (nq <= 0 || rb == 0 || k < 1 || n <= 0) return 0;
   int sm = 148;
   vdb_sm_count(&sm);
   const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, vdb_flat_npad(n), rb / 4, sm);
-  const int64_t segs = plan.n_chunks, bins = nbits + 1;
-  return align256(static_cast<size_t>(segs) * nq * bins * 4) + 4 * align256(static_cast<size_t>(nq) * 4) +
-         2 * align256(static_cast<size_t>(segs) * nq * 4) + align256(static_cast<size_t>(plan.n_qtiles + 1) * 4) +
-         align256(static_cast<size_t>(nq) * k * 8) + 256;
+  const int64_t segs = plan.n_chunks;
+  const int cap = ham_list_cap(n, k, static_cast<int>(segs));
+  return align256(static_cast<size_t>(segs) * nq * cap * 8) + align256(static_cast<size_t>(segs) * nq * 4) +
+         2 * align256(static_cast<size_t>(nq) * 4) + align256(static_cast<size_t>(nq) * (nbits + 1) * 4) +
+         align256(vdb_hamming_topk_workspace_bytes(nq, nbits)) + 256;
 }
 
 int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
@@ -1025,48 +1019,32 @@ int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_
   const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
   const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, n_pad, kpad, sm);
   const int segs = plan.n_chunks, bins = nbits + 1;
+  const int cap = ham_list_cap(n, k, segs);
   uint8_t* w = static_cast<uint8_t*>(workspace);
   size_t off = 0;
-  int* hist = reinterpret_cast<int*>(w + off);   off += align256(static_cast<size_t>(segs) * nq * bins * 4);
-  int* T = reinterpret_cast<int*>(w + off);      off += align256(static_cast<size_t>(nq) * 4);
-  int* bound2 = reinterpret_cast<int*>(w + off); off += align256(static_cast<size_t>(nq) * 4);
-  int* cut = reinterpret_cast<int*>(w + off);    off += align256(static_cast<size_t>(nq) * 4);
-  int* total = reinterpret_cast<int*>(w + off);  off += align256(static_cast<size_t>(nq) * 4);
-  int* take = reinterpret_cast<int*>(w + off);   off += align256(static_cast<size_t>(segs) * nq * 4);
-  int* lbase = reinterpret_cast<int*>(w + off);  off += align256(static_cast<size_t>(segs) * nq * 4);
-  int* active = reinterpret_cast<int*>(w + off); off += align256(static_cast<size_t>(plan.n_qtiles + 1) * 4);
-  uint64_t* list = reinterpret_cast<uint64_t*>(w + off);
+  uint64_t* list = reinterpret_cast<uint64_t*>(w + off); off += align256(static_cast<size_t>(segs) * nq * cap * 8);
+  int* lcnt = reinterpret_cast<int*>(w + off);           off += align256(static_cast<size_t>(segs) * nq * 4);
+  int* T = reinterpret_cast<int*>(w + off);              off += align256(static_cast<size_t>(nq) * 4);
+  uint8_t* fallback = w + off;                           off += align256(static_cast<size_t>(nq) * 4);
+  int* sample_hist = reinterpret_cast<int*>(w + off);    off += align256(static_cast<size_t>(nq) * bins * 4);
+  void* popc_ws = w + off;
 
-  if (hamming_sample_bound(codes, n, qcodes, nq, nbits, k, hist, T, s)) return 3;      // hist doubles as its scratch
-  VDB_CHECK_CUDA(cudaMemsetAsync(hist, 0, static_cast<size_t>(segs) * nq * bins * 4, s));
-  VDB_CHECK_CUDA(cudaMemsetAsync(active, 0, static_cast<size_t>(plan.n_qtiles + 1) * 4, s));
-
+  if (hamming_sample_bound(codes, n, qcodes, nq, nbits, k, sample_hist, T, s)) return 3;
   FlatScanParams P{};
   P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
   P.n_chunks = plan.n_chunks; P.n_pools = plan.n_chunks; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
-  P.tile_stride = 1; P.ham_nbits = nbits; P.ham_hist = hist; P.ham_k = k;
-  const float* bq = static_cast<const float*>(q_bf16);
-  const float* bb = static_cast<const float*>(base_bf16);
+  P.tile_stride = 1; P.ham_nbits = nbits; P.ham_bound = T; P.ham_list = list; P.ham_cnt = lcnt; P.ham_cap = cap;
   CUtensorMap mq, mb;
-  if (make_operand_map(&mq, bq, nq_pad, kpad) || make_operand_map(&mb, bb, n_pad, kpad)) return 3;
-  const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
-
-  P.ham_bound = T;
+  if (make_operand_map(&mq, static_cast<const float*>(q_bf16), nq_pad, kpad) ||
+      make_operand_map(&mb, static_cast<const float*>(base_bf16), n_pad, kpad))
+    return 3;
   if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
-  ham_cut1_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, static_cast<int>(std::min<int64_t>(k, n)), T, bound2, active,
-                                          plan.tile_rows);
-  FlatScanParams R = P;
-  R.ham_bound = bound2; R.qtile_active = active;
-  if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, R, plan.clusters, s)) return 3;
-  ham_cut2_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, T, bound2, cut, take, lbase, total);
-  FlatScanParams C = P;
-  C.ham_bound = cut; C.ham_take = take; C.ham_base = lbase; C.ham_list = list;
-  if (launch_tc<2, true, 32, false, false, 2>(mq, mq, mb, mb, C, plan.clusters, s)) return 3;
-  ham_place_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, static_cast<size_t>(4) * bins * sizeof(int), s>>>(
-      list, total, nq, nbits, k, id_offset, out_d, out_i);
-  count_launches(6);
+  ham_select_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, static_cast<size_t>(4) * (bins + 1) * sizeof(int), s>>>(
+      list, lcnt, segs, cap, nq, nbits, k, static_cast<int>(std::min<int64_t>(k, n)), id_offset, out_d, out_i, fallback);
   VDB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  count_launches(2);
+  // queries whose bound was short or whose lists overflowed: the exact popc path, for them alone
+  return hamming_topk_subset(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, popc_ws, fallback, s);
 }
 
 }  // extern "C"

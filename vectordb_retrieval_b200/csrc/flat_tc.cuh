@@ -48,15 +48,13 @@ struct FlatScanParams {
   int tile_stride;      // base tile visited by step t is t * tile_stride (1 = every tile; > 1 = the strided sample of the pre-pass)
   const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
   float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
-  // Hamming scan (kHam, lsh.cu): operands are bf16 +-1 codes (queries negated, so key = -dot and
-  // ham = (nbits + key) / 2); 1 = count keys <= the per-query bound into hist, 2 = collect keys <= the cut
+  // Hamming scan (kHam, flat.cu): operands are bf16 +-1 codes (queries negated, so key = -dot and
+  // ham = (nbits + key) / 2); every key within the query's bound is appended to the (segment, query) list
   int ham_nbits;
-  const int* ham_bound; // [nq]  mode 1: bound T (-1 = query off); mode 2: cut bin t (-1 = off)
-  int* ham_hist;        // mode 1: [n_chunks][nq][nbits + 1]
-  const int* ham_take;  // mode 2: [n_chunks][nq] ties of bin t this segment keeps (the first ones in row order)
-  const int* ham_base;  // mode 2: [n_chunks][nq] slot of the segment's first entry in the query's list
-  uint64_t* ham_list;   // mode 2: [nq][ham_k] (distance << 32 | row), segment-major
-  int ham_k;
+  const int* ham_bound; // [nq] bound T (-1 = query off)
+  uint64_t* ham_list;   // [n_chunks][nq][ham_cap] (distance << 32 | row), rows ascending inside a segment
+  int* ham_cnt;         // [n_chunks][nq] entries offered to the list (> ham_cap: the list overflowed)
+  int ham_cap;
   int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
 
@@ -288,19 +286,13 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       int cnt = 0;
       float thr = -CUDART_INF_F;
       float top[kSeedKeep];
-      int ham_t = -1, ham_take = 0, ham_seen = 0;
-      int* ham_hist = nullptr;
+      int ham_t = -1;
       uint64_t* ham_out = nullptr;
       if constexpr (kHam != 0) {
         // keys are -dot (integers): ham <= b  <=>  key <= 2b - nbits; the filter compares with `<`
         if (live) ham_t = P.ham_bound[q];
         if (ham_t >= 0) thr = static_cast<float>(2 * ham_t - P.ham_nbits) + 0.5f;
-        if (kHam == 1) {
-          ham_hist = P.ham_hist + (static_cast<int64_t>(chunk) * P.nq + q) * (P.ham_nbits + 1);
-        } else if (ham_t >= 0) {
-          ham_take = P.ham_take[static_cast<int64_t>(chunk) * P.nq + q];
-          ham_out = P.ham_list + q * P.ham_k + P.ham_base[static_cast<int64_t>(chunk) * P.nq + q];
-        }
+        ham_out = P.ham_list + (static_cast<int64_t>(chunk) * P.nq + (live ? q : 0)) * P.ham_cap;
       } else if constexpr (kSeed) {
 #pragma unroll
         for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
@@ -393,16 +385,8 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     const float key = __uint_as_float(v[g * 4 + u]);
                     if (key < thr) {                                   // ham <= bound (padding rows carry +inf)
                       const int ham = (P.ham_nbits + static_cast<int>(key)) >> 1;
-                      if (kHam == 1) {
-                        atomicAdd(ham_hist + ham, 1);
-                      } else {
-                        const bool tie = ham == ham_t;
-                        if (!tie || ham_seen < ham_take) {
-                          ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
-                          ++cnt;
-                        }
-                        ham_seen += tie ? 1 : 0;
-                      }
+                      if (cnt < P.ham_cap) ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
+                      ++cnt;
                     }
                   }
                 }
@@ -445,6 +429,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         __syncwarp();                              // all lanes are done with this tile's norms
         if (lane == 0) mbar_arrive(norm_empty_bar + buf);
         if (!kSeed && kHam == 0 && live) thr = fminf(thr, ord2f(thr_seen));
+      }
+      if constexpr (kHam != 0) {
+        if (live) P.ham_cnt[static_cast<int64_t>(chunk) * P.nq + q] = cnt;
       }
       if constexpr (kSeed) {
         float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);

@@ -125,7 +125,10 @@ __global__ void hamming_bound_kernel(const int* __restrict__ hist, int64_t nq, i
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   const int bins = nbits + 1;
-  const double need = (1.25 * k + 16.0) * static_cast<double>(s) / static_cast<double>(n);
+  // expected sample rows among the k nearest, plus four standard deviations of that (Poisson) count:
+  // a flat 25 % margin left 13 % of the queries short at k = 800 (22 expected sample rows)
+  const double lam = static_cast<double>(k) * static_cast<double>(s) / static_cast<double>(n);
+  const double need = lam + 4.0 * sqrt(lam) + 4.0;
   long long cum = 0;
   int t = nbits;
   for (int b = 0; b < bins; ++b) {
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(128)
 hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, int64_t seg_len, const uint4* __restrict__ qcodes,
                     int64_t nq, int nbits, const int* __restrict__ cut, const int* __restrict__ take,
                     const int* __restrict__ offs, int k, int64_t id_offset, float* __restrict__ out_d,
-                    int64_t* __restrict__ out_i) {
+                    int64_t* __restrict__ out_i, const uint8_t* __restrict__ only) {
   constexpr int QT = queries_per_warp<W4>();
   extern __shared__ int smem_i[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,10 +211,16 @@ hamming_emit_kernel(const uint4* __restrict__ codes, int64_t n, int64_t seg_len,
   int* cursor = smem_i + warp * QT * bins;
   uint4 qc[QT][W4];
   int cq[QT], rq[QT], seen[QT];
+  if (only != nullptr) {                               // subset run: warps without a flagged query have nothing to do
+    bool any = false;
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) any |= q0 + qi < nq && only[q0 + qi] != 0;
+    if (!any) return;
+  }
 #pragma unroll
   for (int qi = 0; qi < QT; ++qi) {
     const int64_t q = q0 + qi;
-    const bool live = q < nq;
+    const bool live = q < nq && (only == nullptr || only[q] != 0);
     cq[qi] = live ? cut[q] : -1;
     rq[qi] = live ? seg_take[q] : 0;
     seen[qi] = 0;
@@ -308,7 +317,7 @@ static int run_hamming(const uint32_t* codes, int64_t n, const uint32_t* qcodes,
     hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, T, redo, cut, take, nullptr);
     count_launches(6);
   }
-  emit<<<grid, 128, smem, s>>>(c4, n, seg_len, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i);
+  emit<<<grid, 128, smem, s>>>(c4, n, seg_len, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i, nullptr);
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -331,6 +340,50 @@ static int sample_bound_impl(const uint32_t* codes, int64_t n, const uint32_t* q
   count_launches(2);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// exact popc path for the queries flagged in `only` (all others are left untouched): full count, cut, emission
+template <int W4>
+static int subset_impl(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                       int64_t id_offset, float* out_d, int64_t* out_i, void* ws, const uint8_t* only, cudaStream_t s) {
+  constexpr int QT = queries_per_warp<W4>();
+  const int bins = nbits + 1;
+  const int segs = hamming_segments(n, nq, QT);
+  const int64_t seg_len = ((n + segs - 1) / segs + 31) / 32 * 32;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  int* hist = reinterpret_cast<int*>(w);
+  size_t off = al(static_cast<size_t>(segs) * nq * bins * 4);
+  int* take = reinterpret_cast<int*>(w + off); off += al(static_cast<size_t>(segs) * nq * 4);
+  off += al(static_cast<size_t>(nq) * 4);
+  int* cut = reinterpret_cast<int*>(w + off);
+  const uint4* c4 = reinterpret_cast<const uint4*>(codes);
+  const uint4* q4 = reinterpret_cast<const uint4*>(qcodes);
+  const unsigned blocks = static_cast<unsigned>((nq + 4 * QT - 1) / (4 * QT));
+  const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
+  const size_t smem = static_cast<size_t>(4) * QT * bins * sizeof(int);
+  auto count = hamming_count_kernel<W4>;
+  auto emit = hamming_emit_kernel<W4>;
+  if (smem > 48 * 1024) {
+    VDB_CHECK_CUDA(cudaFuncSetAttribute(count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    VDB_CHECK_CUDA(cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  const dim3 grid(blocks, segs);
+  count<<<grid, 128, smem, s>>>(c4, 0, n, seg_len, q4, nq, nbits, nullptr, only, hist);
+  hamming_cut_kernel<<<qblocks, 256, 0, s>>>(hist, segs, nq, nbits, k, nullptr, only, cut, take, nullptr);
+  emit<<<grid, 128, smem, s>>>(c4, n, seg_len, q4, nq, nbits, cut, take, hist, k, id_offset, out_d, out_i, only);
+  count_launches(3);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int hamming_topk_subset(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
+                        int64_t id_offset, float* out_d, int64_t* out_i, void* ws, const uint8_t* only, cudaStream_t stream) {
+  switch (vdb_lsh_code_words(nbits) / 4) {
+    case 1: return subset_impl<1>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, ws, only, stream);
+    case 2: return subset_impl<2>(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, ws, only, stream);
+    default: set_error("hamming_topk_subset: nbits %d not supported", nbits); return 2;
+  }
 }
 
 int hamming_sample_bound(const uint32_t* codes, int64_t n, const uint32_t* qcodes, int64_t nq, int nbits, int k,
