@@ -26,7 +26,7 @@ def short(name: str) -> str:
         parts = args.split(",")
         seed = len(parts) >= 5 and parts[4] == "1"
         ham = parts[5] if len(parts) >= 6 else "0"
-        kind = " (seeding pre-pass)" if seed else {"1": " (Hamming count)", "2": " (Hamming collect)"}.get(ham, " (main scan)")
+        kind = " (seeding pre-pass)" if seed else {"1": " (Hamming scan: bf16 codes, collect within the bound)"}.get(ham, " (main scan)")
         return "flat_scan_tc_kernel<" + args + ">" + kind
     for cut in ("<", "("):
         if cut in name:
