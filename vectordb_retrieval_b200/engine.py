@@ -426,7 +426,8 @@ class HammingShard:
     """Sign-projection codes of one GPU's rows + the Hamming top-k scan (``faiss.IndexLSH``).
 
     HBM layout: ``codes`` [n, words] int32 (words = 4 * ceil(nbits / 128), 32 bytes per row at 256
-    bits) and the transposed projection [d, words * 32]."""
+    bits) and the transposed projection [d, words * 32]; large bases with nbits <= 256 also keep the
+    codes as bf16 +-1 rows (512 bytes per row at 256 bits) for the tensor-pipe scan, built on first use."""
 
     def __init__(self, vectors, projection: np.ndarray, device=None, id_offset: int = 0, upload_rows: int = 1 << 20):
         self.lib = _lib.load()
@@ -467,7 +468,9 @@ class HammingShard:
             out[:, :native].copy_(tmp)
 
     def memory_bytes(self) -> int:
-        return self.codes.numel() * 4 + self.proj_t.numel() * 4
+        expanded = getattr(self, "_bf16", None)           # bf16 copies for the tensor-pipe scan, built on first use
+        extra = 0 if expanded is None else expanded[0].numel() + expanded[1].numel() * 4
+        return self.codes.numel() * 4 + self.proj_t.numel() * 4 + extra
 
     def state(self) -> Dict[str, np.ndarray]:
         return {"codes": self.codes.cpu().numpy(), "proj_t": self.proj_t.cpu().numpy(),
