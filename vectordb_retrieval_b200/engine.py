@@ -527,6 +527,8 @@ class HammingShard:
             return False
         if self.words != self.lib.vdb_lsh_code_words(self.nbits) or self.n <= 65536 or k > self.n:
             return False
+        if self.lib.vdb_hamming_tc_workspace_bytes(nq, self.nbits, k, self.n) > (8 << 30):
+            return False                                   # candidate lists of huge batches: stay on the popc kernels
         return True if self.tensor_pipe is True else (nq >= 256 and self.n <= 8_000_000)
 
     def _expanded(self) -> Tuple[torch.Tensor, torch.Tensor]:
