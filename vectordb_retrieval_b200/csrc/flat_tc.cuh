@@ -382,12 +382,13 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 if (um & (1u << g)) {
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
+                    // branch-free like the flat scan's appends: the per-key test only predicates the store
                     const float key = __uint_as_float(v[g * 4 + u]);
-                    if (key < thr) {                                   // ham <= bound (padding rows carry +inf)
-                      const int ham = (P.ham_nbits + static_cast<int>(key)) >> 1;
-                      if (cnt < P.ham_cap) ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
-                      ++cnt;
-                    }
+                    const bool hit = key < thr;                        // ham <= bound (padding rows carry +inf)
+                    const int ham = (P.ham_nbits + __float2int_rz(fminf(key, 1024.f))) >> 1;
+                    if (hit && cnt < P.ham_cap)
+                      ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
+                    cnt += hit ? 1 : 0;
                   }
                 }
               }
