@@ -20,6 +20,16 @@
 //                               the (query, chunk, group) pool
 // kCtaGroup == 2: two CTAs of a cluster form one 256 x 256 UMMA (cta_group::2); each loads half
 // of every base tile, which halves L2->smem traffic per SM.
+//
+// The same pipeline runs with four other epilogues (template flags; the host side is in flat.cu):
+//   kSeed   seeding pre-pass over a strided sample of base tiles: one TF32 product, no candidates,
+//           the 16 smallest 32-row chunk minima per (query, item) in registers -> starting bounds
+//   (redo)  P.qtile_active: a launch that runs only the query tiles flagged by the verify kernel
+//   kDense  writes the key matrix; with P.dense_only it keeps no candidates (small bases: the
+//           selection is a separate kernel) - otherwise the test hook for the 3xTF32 keys
+//   kHam    Hamming scan: bf16 +-1 code rows (the byte geometry of a 128-float row), one kind::f16
+//           MMA group per k-block, every key within the query's sampled bound appended to a
+//           (segment, query) list
 #pragma once
 #include <cuda.h>
 
