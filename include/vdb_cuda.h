@@ -142,6 +142,13 @@ int vdb_flat_timing_read(float* ms, int max_records, int* n_out);
  * result does not depend on the number of parts.  `descending` for raw-IP (+score) lists. */
 int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t nq, int k,
                    int descending, float pad_value, float* out_d, int64_t* out_i, void* stream);
+/* Same merge over parts that are not densely packed: part p's lists start at d_all + p * stride_d and
+ * i_all + p * stride_i (strides in elements, >= nq * k).  This is what lets ONE collective carry both
+ * arrays (each rank's block = [distances | ids]) and lets a rank merge only a slice of the queries
+ * (pass pointers offset to the slice's first query and keep the strides). */
+int vdb_merge_topk_strided(const float* d_all, const int64_t* i_all, int64_t stride_d, int64_t stride_i,
+                           int parts, int64_t nq, int k, int descending, float pad_value,
+                           float* out_d, int64_t* out_i, void* stream);
 
 /* ---- candidate re-ranking (LSH) ------------------------------------------------------- */
 /* base [n,d] fp32 row-major (ld elements, ld % 4 == 0, 16-byte aligned), cand [nq,C] int64

@@ -97,7 +97,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _gloo_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+def _gloo_worker(rank: int, world: int, port: int, out_dir: str, nq: int) -> None:
     import torch
     import torch.distributed as dist
     from vectordb_retrieval_b200 import sharded
@@ -105,37 +105,59 @@ def _gloo_worker(rank: int, world: int, port: int, out_dir: str) -> None:
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.RandomState(0)
     base = rng.randn(3001, 16).astype(np.float32)
-    queries = rng.randn(37, 16).astype(np.float32)
+    queries = rng.randn(nq, 16).astype(np.float32)
     plan = sharded.ShardPlan(base.shape[0], world)
     lo, hi = plan.start(rank), plan.stop(rank)
 
-    def local_search(q, k):                      # stands in for the CUDA shard: oracle on this rank's rows
+    def local_search(q, k, out):                 # stands in for the CUDA shard: oracle on this rank's rows
         d, i = oracle.faiss_flat_search(base[lo:hi], q, k, "l2")
-        i = np.where(i >= 0, i + lo, -1)
-        return torch.from_numpy(d), torch.from_numpy(i)
+        out[0].copy_(torch.from_numpy(d))
+        out[1].copy_(torch.from_numpy(np.where(i >= 0, i + lo, -1)))
 
-    def merge(d_all, i_all):                     # stands in for vdb_merge_topk
-        d, i = oracle.merge_topk([x.numpy() for x in d_all], [x.numpy() for x in i_all], d_all.shape[2])
-        return torch.from_numpy(d), torch.from_numpy(i)
+    def merge(d_parts, i_parts, out):            # stands in for vdb_merge_topk_strided (parts are strided views)
+        d, i = oracle.merge_topk([x.numpy() for x in d_parts], [x.numpy() for x in i_parts], d_parts.shape[2])
+        if out is None:
+            return torch.from_numpy(d), torch.from_numpy(i)
+        out[0].copy_(torch.from_numpy(d))
+        out[1].copy_(torch.from_numpy(i))
+        return out
 
     assert sharded.dist_info() == (rank, world)
-    d, i = sharded.ShardedTopK(local_search, sharded.allgather_topk, merge).search(queries, 25)
-    np.save(os.path.join(out_dir, f"d{rank}.npy"), d.numpy())
-    np.save(os.path.join(out_dir, f"i{rank}.npy"), i.numpy())
+    for exchange in ("allgather", "alltoall"):
+        plan_x = sharded.ShardedTopK(local_search, merge, exchange, "cpu")
+        for rep in range(2):                     # second call reuses the exchange buffers
+            d, i = plan_x.search(queries, 25)
+        np.save(os.path.join(out_dir, f"d_{exchange}{rank}.npy"), d.numpy())
+        np.save(os.path.join(out_dir, f"i_{exchange}{rank}.npy"), i.numpy())
+    # host path: each rank publishes only its merged query slice into the shared block; ring of 4 slots
+    kept = []
+    for rep in range(6):
+        dh, ih = plan_x.search_to_host(queries + np.float32(rep >= 5), 25)
+        kept.append((dh, ih))
+    np.save(os.path.join(out_dir, f"d_host{rank}.npy"), kept[4][0])
+    np.save(os.path.join(out_dir, f"i_host{rank}.npy"), kept[4][1])
+    assert not np.shares_memory(kept[4][1], kept[5][1]) and np.shares_memory(kept[1][1], kept[5][1])
+    dist.barrier()
+    for hb in plan_x._host.values():
+        hb.close()
     dist.destroy_process_group()
 
 
-def test_sharded_search_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("world,nq", [(2, 37), (3, 2)])
+def test_sharded_search_gloo(tmp_path, world, nq):
+    """Row-sharded search over `world` gloo ranks: both exchange plans and the shared-host-block path return the
+    single-index result on every rank (nq = 2 < world leaves ranks with empty query slices)."""
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path), nq), nprocs=world, join=True)
     rng = np.random.RandomState(0)
     base = rng.randn(3001, 16).astype(np.float32)
-    queries = rng.randn(37, 16).astype(np.float32)
+    queries = rng.randn(nq, 16).astype(np.float32)
     ref_d, ref_i = oracle.faiss_flat_search(base, queries, 25, "l2")
-    for rank in range(2):
-        np.testing.assert_array_equal(np.load(tmp_path / f"i{rank}.npy"), ref_i)
-        np.testing.assert_allclose(np.load(tmp_path / f"d{rank}.npy"), ref_d, rtol=1e-6)
+    for rank in range(world):
+        for tag in ("allgather", "alltoall", "host"):
+            np.testing.assert_array_equal(np.load(tmp_path / f"i_{tag}{rank}.npy"), ref_i, err_msg=f"{tag} rank {rank}")
+            np.testing.assert_allclose(np.load(tmp_path / f"d_{tag}{rank}.npy"), ref_d, rtol=1e-6)
 
 
 def test_reference_registry_plugin_if_reference_present():

@@ -48,11 +48,17 @@ dist.init_process_group("nccl", device_id=dev)
 import vectordb_retrieval_b200.algorithms as A
 rng = np.random.RandomState(3)
 base = rng.randn(30011, 48).astype(np.float32); queries = rng.randn(257, 48).astype(np.float32)
-for mode in ("rows", "queries"):              # row shards + merge kernel / replicated base + query slices
-    algo = A.get_algorithm_instance("ExactSearch", 48, name="dist", metric="l2", device=dev, shard=mode)
+for mode, exchange in (("rows", "alltoall"), ("rows", "allgather"), ("queries", "alltoall")):
+    # row shards + packed exchange + merge kernel (both exchange plans) / replicated base + query slices
+    algo = A.get_algorithm_instance("ExactSearch", 48, name="dist", metric="l2", device=dev, shard=mode, exchange=exchange)
     algo.build_index(base)
-    d, i = algo.batch_search(queries, 50)
-    np.save(os.path.join({out!r}, f"d_{{mode}}{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i_{{mode}}{{rank}}.npy"), i)
+    tag = mode if exchange == "alltoall" else mode + "_" + exchange
+    for rep in range(2):                      # host path: results land in the ranks' shared pinned block
+        d, i = algo.batch_search(queries, 50)
+    np.save(os.path.join({out!r}, f"d_{{tag}}{{rank}}.npy"), d); np.save(os.path.join({out!r}, f"i_{{tag}}{{rank}}.npy"), i)
+    dd, ii = algo.index.search_device(torch.from_numpy(queries).to(dev), 50)      # device path: result on every rank
+    np.save(os.path.join({out!r}, f"d_{{tag}}_dev{{rank}}.npy"), dd.cpu().numpy()); np.save(os.path.join({out!r}, f"i_{{tag}}_dev{{rank}}.npy"), ii.cpu().numpy())
+    del algo
 # IVF-Flat with replicated centroids and row-sharded lists: same answer as one GPU holding every list
 from vectordb_retrieval_b200 import engine, sharded
 ivf = sharded.DistributedIVFIndex.from_global(base, 64, "l2", dev, nprobe=8)
@@ -82,13 +88,18 @@ def test_distributed_flat_index_nccl(tmp_path):
     base = rng.randn(30011, 48).astype(np.float32)
     queries = rng.randn(257, 48).astype(np.float32)
     ref = oracle.faiss_flat_search(base, queries, 50, "l2")
-    for mode in ("rows", "queries"):
+    for mode in ("rows", "rows_allgather", "queries"):
         for r in range(n):
-            res = oracle.compare_topk(ref[0], ref[1], np.load(tmp_path / f"d_{mode}{r}.npy"), np.load(tmp_path / f"i_{mode}{r}.npy"),
-                                      rtol=1e-5)
-            assert res["ok"], (mode, r, res)
+            for path in ("", "_dev"):         # host path (shared pinned block) and device path
+                res = oracle.compare_topk(ref[0], ref[1], np.load(tmp_path / f"d_{mode}{path}{r}.npy"),
+                                          np.load(tmp_path / f"i_{mode}{path}{r}.npy"), rtol=1e-5)
+                assert res["ok"], (mode, path, r, res)
+            np.testing.assert_array_equal(np.load(tmp_path / f"i_{mode}{r}.npy"), np.load(tmp_path / f"i_{mode}_dev{r}.npy"))
+            np.testing.assert_array_equal(np.load(tmp_path / f"d_{mode}{r}.npy"), np.load(tmp_path / f"d_{mode}_dev{r}.npy"))
         np.testing.assert_array_equal(np.load(tmp_path / f"i_{mode}0.npy"), np.load(tmp_path / f"i_{mode}{n - 1}.npy"))
     np.testing.assert_array_equal(np.load(tmp_path / "i_rows0.npy"), np.load(tmp_path / "i_queries0.npy"))
+    np.testing.assert_array_equal(np.load(tmp_path / "i_rows0.npy"), np.load(tmp_path / "i_rows_allgather0.npy"))
+    np.testing.assert_array_equal(np.load(tmp_path / "d_rows0.npy"), np.load(tmp_path / "d_rows_allgather0.npy"))
     for r in range(n):        # sharded IVF == single-GPU IVF with the same centroids, on every rank
         np.testing.assert_array_equal(np.load(tmp_path / f"i_ivf{r}.npy"), np.load(tmp_path / "i_ivf_single.npy"))
         np.testing.assert_array_equal(np.load(tmp_path / f"d_ivf{r}.npy"), np.load(tmp_path / "d_ivf_single.npy"))

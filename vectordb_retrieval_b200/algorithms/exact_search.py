@@ -32,7 +32,8 @@ class ExactSearch(BaseAlgorithm):
             raise RuntimeError(f"expected vectors of shape [n, {self.dimension}], got {vectors.shape}")
         self.vectors = vectors          # the harness' array; never mutated (dtype/layout fixed on upload)
         self.index = GpuIndexFlat(self.dimension, self.metric, device=self.config.get("device"),
-                                  devices=self.config.get("devices"), shard=self.config.get("shard", "auto"))
+                                  devices=self.config.get("devices"), shard=self.config.get("shard", "auto"),
+                                  exchange=self.config.get("exchange", "alltoall"))
         self.index.add(vectors)
         self.index_built = True
 

@@ -397,8 +397,9 @@ flat_finalize_kernel(int metric, const float* __restrict__ b_hi, const float* __
 // Merge of per-shard sorted lists after the allgather: one warp per query, (distance, id) order.
 template <int KP>
 __global__ void __launch_bounds__(128)
-merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i_all, int parts, int64_t nq,
-                  int k, int descending, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i_all, int64_t stride_d, int64_t stride_i,
+                  int parts, int64_t nq, int k, int descending, float pad_value, float* __restrict__ out_d,
+                  int64_t* __restrict__ out_i) {
   // Candidates are keyed (value, position) with position = part*k + rank.  Parts arrive in
   // ascending id-range order (row-sharded base, allgather in rank order) and every part is
   // already sorted by (value, id), so (value, position) order IS (value, id) order: the merged
@@ -419,9 +420,9 @@ merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i
       uint64_t w = kEmpty;
       if (pos < total) {
         const int p = pos / k, r = pos % k;
-        const int64_t off = (static_cast<int64_t>(p) * nq + q) * k + r;
-        if (i_all[off] >= 0) {
-          const float val = d_all[off];
+        const int64_t off = q * k + r;
+        if (i_all[p * stride_i + off] >= 0) {
+          const float val = d_all[p * stride_d + off];
           w = pack_key(descending ? -val : val, static_cast<uint32_t>(pos));
         }
       }
@@ -437,9 +438,9 @@ merge_topk_kernel(const float* __restrict__ d_all, const int64_t* __restrict__ i
       int64_t iv = -1;
       if (best[e] != kEmpty) {
         const int pos = static_cast<int>(packed_row(best[e]));
-        const int64_t off = (static_cast<int64_t>(pos / k) * nq + q) * k + pos % k;
-        dv = d_all[off];
-        iv = i_all[off];
+        const int64_t off = q * k + pos % k;
+        dv = d_all[(pos / k) * stride_d + off];
+        iv = i_all[(pos / k) * stride_i + off];
       }
       out_d[q * k + r] = dv;
       out_i[q * k + r] = iv;
@@ -950,23 +951,31 @@ int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, in
   return 0;
 }
 
-int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t nq, int k, int descending,
-                   float pad_value, float* out_d, int64_t* out_i, void* stream) {
+int vdb_merge_topk_strided(const float* d_all, const int64_t* i_all, int64_t stride_d, int64_t stride_i, int parts,
+                           int64_t nq, int k, int descending, float pad_value, float* out_d, int64_t* out_i, void* stream) {
   VDB_REQUIRE(parts >= 1 && nq > 0 && k >= 1, "vdb_merge_topk: bad shape");
+  VDB_REQUIRE(stride_d >= nq * k && stride_i >= nq * k, "vdb_merge_topk: part stride smaller than nq * k");
   const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
   VDB_REQUIRE(kp != 0, "vdb_merge_topk: k=%d unsupported (<= 512)", k);
   VDB_REQUIRE(static_cast<int64_t>(parts) * k < (int64_t(1) << 31), "vdb_merge_topk: parts*k too large");
   const unsigned blocks = static_cast<unsigned>((nq + 3) / 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define VDB_GO(KP) merge_topk_kernel<KP><<<blocks, 128, 0, s>>>(d_all, i_all, stride_d, stride_i, parts, nq, k, descending, pad_value, out_d, out_i)
   switch (kp) {
-    case 32: merge_topk_kernel<32><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
-    case 128: merge_topk_kernel<128><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
-    case 256: merge_topk_kernel<256><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
-    default: merge_topk_kernel<512><<<blocks, 128, 0, s>>>(d_all, i_all, parts, nq, k, descending, pad_value, out_d, out_i); break;
+    case 32: VDB_GO(32); break;
+    case 128: VDB_GO(128); break;
+    case 256: VDB_GO(256); break;
+    default: VDB_GO(512); break;
   }
+#undef VDB_GO
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int vdb_merge_topk(const float* d_all, const int64_t* i_all, int parts, int64_t nq, int k, int descending,
+                   float pad_value, float* out_d, int64_t* out_i, void* stream) {
+  return vdb_merge_topk_strided(d_all, i_all, nq * k, nq * k, parts, nq, k, descending, pad_value, out_d, out_i, stream);
 }
 
 int vdb_hamming_tc_row_bytes(int nbits) { return nbits <= 0 || nbits > 256 ? 0 : (nbits + 63) / 64 * 128; }

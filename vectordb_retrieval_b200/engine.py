@@ -222,17 +222,26 @@ class FlatShard:
         return keys[:nq, :self.n]
 
 
-def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, descending: bool = False, pad_value: float = FLT_MAX
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[parts, nq, k] gathered shard results -> merged [nq, k] (parts in ascending id order)."""
+def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, descending: bool = False, pad_value: float = FLT_MAX,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[parts, nq, k] gathered shard results -> merged [nq, k] (parts in ascending id order).  The parts may be
+    strided views (one packed exchange buffer per rank, a slice of the queries): only the [nq, k] block of a
+    part has to be dense."""
     lib = _lib.load()
     parts, nq, k = d_all.shape
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=d_all.device)
-    out_i = torch.empty((nq, k), dtype=torch.int64, device=d_all.device)
+    for t in (d_all, i_all):
+        if t.stride(2) != 1 or t.stride(1) != k:
+            raise RuntimeError("merge_topk: every part must be a dense [nq, k] block")
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.float32, device=d_all.device),
+               torch.empty((nq, k), dtype=torch.int64, device=d_all.device))
+    if nq == 0:
+        return out
     with torch.cuda.device(d_all.device):
-        check(lib.vdb_merge_topk(ptr(d_all), ptr(i_all), parts, nq, k, int(descending), pad_value, ptr(out_d), ptr(out_i),
-                                 _stream(d_all.device)), "vdb_merge_topk")
-    return out_d, out_i
+        check(lib.vdb_merge_topk_strided(ptr(d_all), ptr(i_all), d_all.stride(0) if parts > 1 else nq * k,
+                                         i_all.stride(0) if parts > 1 else nq * k, parts, nq, k, int(descending), pad_value,
+                                         ptr(out[0]), ptr(out[1]), _stream(d_all.device)), "vdb_merge_topk")
+    return out
 
 
 def pad_cols(x: torch.Tensor, multiple: int = 4) -> torch.Tensor:

@@ -32,8 +32,10 @@ def _metric_name(metric) -> str:
 class GpuIndexFlat:
     """``faiss.IndexFlat(d, metric)``: exact search on one GPU, or row-sharded over several."""
 
-    def __init__(self, d: int, metric="l2", device=None, devices=None, normalize: bool = False, shard: str = "auto"):
+    def __init__(self, d: int, metric="l2", device=None, devices=None, normalize: bool = False, shard: str = "auto",
+                 exchange: str = "alltoall"):
         self.shard = shard                    # under torchrun: 'rows', 'queries' (replicated base) or 'auto'
+        self.exchange = exchange              # rows layout: 'alltoall' or 'allgather' (sharded.TopKExchange)
         self.d = int(d)
         self.metric = _metric_name(metric)
         self.normalize = bool(normalize)      # cosine: rows and queries are L2-normalised on the device
@@ -56,7 +58,7 @@ class GpuIndexFlat:
         if world > 1 and sharded.choose_sharding(int(x.shape[0]), (self.d + 31) // 32 * 32, world, self.shard) == "queries":
             self._impl = sharded.ReplicatedFlatIndex(x, metric, self.device)
         elif world > 1:
-            self._impl = sharded.DistributedFlatIndex.from_global(x, metric, self.device)
+            self._impl = sharded.DistributedFlatIndex.from_global(x, metric, self.device, exchange=self.exchange)
         elif self.devices is not None and len(self.devices) > 1:
             self._impl = sharded.MultiDeviceFlatIndex(x, metric, self.devices)
         else:
@@ -100,9 +102,9 @@ class GpuIndexFlat:
         if self._impl is None:
             raise RuntimeError("index is empty")
         with torch.cuda.device(self.home):
-            if hasattr(self._impl, "search_host"):      # replicated base: only this rank's query slice crosses PCIe
+            if hasattr(self._impl, "search_host"):      # one process per GPU: each rank moves only its query slice of the result
                 pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
-                return engine.results_to_host(*self._impl.search_host(queries, int(k), 0, pad))
+                return self._impl.search_host(queries, int(k), 0, pad)
             q = engine.queries_to_device(queries, self.home, self.d)
             return engine.results_to_host(*self.search_device(q, int(k)))
 

@@ -24,6 +24,24 @@ import types
 from typing import Any, Dict, Optional
 
 
+class _Inert:
+    """Stand-in object for the plotting calls of the reference (src/benchmark/evaluation.py:162-276,
+    src/experiments/experiment_runner.py:764-780): every attribute is a callable that returns another
+    inert object, so ``fig, ax = plt.subplots(); ax.scatter(...); plt.savefig(path)`` runs and draws
+    nothing.  Plots are cosmetic; the result JSON / Markdown are written before them."""
+
+    def __call__(self, *args: Any, **kwargs: Any) -> "_Inert":
+        return self
+
+    def __getattr__(self, name: str) -> "_Inert":
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return self
+
+    def __iter__(self):
+        return iter(())
+
+
 def _stub_missing_modules() -> None:
     try:
         importlib.import_module("faiss")
@@ -34,9 +52,12 @@ def _stub_missing_modules() -> None:
     try:
         importlib.import_module("matplotlib.pyplot")
     except ImportError:
+        inert = _Inert()
         mpl = types.ModuleType("matplotlib")
         mpl.use = lambda *a, **k: None
         plt = types.ModuleType("matplotlib.pyplot")
+        plt.subplots = lambda *a, **k: (inert, inert)
+        plt.__getattr__ = lambda name: inert           # module-level __getattr__ (PEP 562): figure, savefig, close, ...
         mpl.pyplot = plt
         sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
 
@@ -67,3 +88,22 @@ def install(modules: Optional[Dict[str, Any]] = None) -> None:
         cls = ours.SEARCHER_REGISTRY[name]
         ref_modular.register_searcher(name, cls)
         ref_modular.BaseSearcher.register(cls)
+
+
+def run_reference_cli(root: str, argv: Optional[list] = None) -> int:
+    """Run the reference's own ``scripts/run_full_benchmark.py`` (file untouched, its ``main()`` called as
+    ``python scripts/run_full_benchmark.py <argv>`` would) with the CUDA classes installed first.
+    ``root`` = the reference checkout (``baseline/_ref`` after ``scripts/stage_reference.py``)."""
+    import importlib.util
+    import os
+    install(import_reference(root))
+    path = os.path.join(root, "scripts", "run_full_benchmark.py")
+    spec = importlib.util.spec_from_file_location("_reference_run_full_benchmark", path)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)                    # imports src.benchmark.runner of the reference
+    old_argv = sys.argv
+    sys.argv = [path] + list(argv or [])
+    try:
+        return int(module.main() or 0)
+    finally:
+        sys.argv = old_argv
