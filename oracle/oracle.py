@@ -519,6 +519,68 @@ def ivf_flat_search(base: np.ndarray, centroids: np.ndarray, assignments: np.nda
     return out_d, out_i, probes
 
 
+# --------------------------------------------------------------------------- IVF training (k-means recipe)
+def kmeans_lloyd_step(sample: np.ndarray, cent: np.ndarray, spherical: bool) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """One Lloyd iteration in fp64: nearest centroid (L2, or largest inner product when ``spherical``; ties to
+    the lowest centroid index), mean per cluster, empty clusters re-seeded by splitting the most populated one
+    with the +-1/1024 sign pattern (the FAISS ``Clustering`` rule [FAISS-upstream], reached from
+    ``index.train`` at src/algorithms/modular.py:281-282), spherical centroids re-normalised.
+    Returns (new centroids float32, assignment, cluster sizes before the split)."""
+    x = np.asarray(sample, dtype=np.float64)
+    c = np.asarray(cent, dtype=np.float64)
+    nlist, d = c.shape
+    assign = np.empty(x.shape[0], dtype=np.int64)
+    cn = (c ** 2).sum(axis=1)
+    for s in range(0, x.shape[0], 65536):
+        ip = x[s:s + 65536] @ c.T
+        key = -ip if spherical else cn[None, :] - 2.0 * ip
+        assign[s:s + 65536] = np.argmin(key, axis=1)
+    sizes = np.bincount(assign, minlength=nlist).astype(np.int64)
+    sums = np.zeros((nlist, d))
+    np.add.at(sums, assign, x)
+    new = (sums / np.maximum(sizes, 1)[:, None]).astype(np.float32)
+    cnt = sizes.copy()
+    for e in np.nonzero(cnt == 0)[0].tolist():
+        big = int(np.argmax(cnt))
+        eps = 1.0 / 1024.0
+        sign = np.where(np.arange(d) % 2 == 0, 1.0 + eps, 1.0 - eps).astype(np.float32)
+        new[e] = new[big] * sign
+        new[big] = new[big] * (2.0 - sign)
+        cnt[e] = cnt[big] // 2
+        cnt[big] -= cnt[e]
+    if spherical:
+        new = safe_normalize(new)
+    return new, assign, sizes
+
+
+def kmeans_lloyd(vectors: np.ndarray, nlist: int, metric: str = "l2", niter: int = 10, seed: int = 1234,
+                 max_points_per_centroid: int = 256) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """The IVF training recipe of ``engine.kmeans_train`` restated on the CPU in fp64 - what replaces
+    ``index.train(data)`` (src/algorithms/modular.py:281-282; FAISS k-means itself is not reproducible here:
+    parity unpinned vs FAISS).  Same draw order: ``RandomState(seed)``; if n > 256 * nlist a sorted sample of
+    that many rows without replacement; ``nlist`` sorted distinct sample rows as starting centroids; ``niter``
+    Lloyd iterations.  cosine: rows normalised first; ip / cosine: spherical.
+    Returns (centroids, sample rows, inertia per iteration = mean squared distance / mean (1 - cos))."""
+    v = _as_f32(vectors)
+    n = v.shape[0]
+    rng = np.random.RandomState(seed)
+    limit = max_points_per_centroid * nlist
+    rows = np.sort(rng.choice(n, limit, replace=False)) if n > limit else np.arange(n)
+    init = np.sort(rng.permutation(rows.shape[0])[:nlist])
+    sample = v[rows]
+    if metric == "cosine":
+        sample = safe_normalize(sample)
+    spherical = metric != "l2"
+    cent = sample[init].copy()
+    inertia = []
+    for _ in range(niter):
+        new, assign, _ = kmeans_lloyd_step(sample, cent, spherical)
+        diff = sample.astype(np.float64) - cent.astype(np.float64)[assign]
+        inertia.append(float((diff ** 2).sum(axis=1).mean()))
+        cent = new
+    return cent, rows, np.asarray(inertia)
+
+
 # --------------------------------------------------------------------------- multi-shard merge
 def merge_topk(dists: Sequence[np.ndarray], ids: Sequence[np.ndarray], k: int,
                ascending: bool = True) -> Tuple[np.ndarray, np.ndarray]:

@@ -93,6 +93,19 @@ def normalize_rows_(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def normalized_rows(x: torch.Tensor) -> torch.Tensor:
+    """Row-normalised COPY (zero rows stay zero): the caller's tensor is never written.  Used wherever the input
+    may alias user data (a base or query batch handed over as a device tensor)."""
+    lib = _lib.load()
+    y = torch.empty((x.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    if x.shape[0] == 0:
+        return y
+    with torch.cuda.device(x.device):
+        check(lib.vdb_normalize_rows(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(y), y.stride(0), _stream(x.device)),
+              "vdb_normalize_rows")
+    return y
+
+
 def row_norms(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
@@ -126,7 +139,7 @@ class FlatShard:
             for s in range(0, n, upload_rows):
                 blk = to_device_f32(vectors[s:s + upload_rows], self.dev)
                 if metric == "cosine":
-                    normalize_rows_(blk)
+                    blk = normalized_rows(blk)             # a copy: `vectors` may be the caller's device tensor
                 m = blk.shape[0]
                 check(self.lib.vdb_flat_prepare(ptr(blk), m, d, blk.stride(0), metric_code(metric),
                                                 self.hi[s:].data_ptr(), self.lo[s:].data_ptr(), self.norms[s:].data_ptr(),
@@ -184,9 +197,9 @@ class FlatShard:
         return buf
 
     def prepare_queries(self, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """q: [nq, d] fp32 device tensor (normalised in place for cosine)."""
+        """q: [nq, d] fp32 device tensor; never written (cosine normalises a copy)."""
         if self.metric == "cosine":
-            normalize_rows_(q)
+            q = normalized_rows(q)
         q_hi, q_lo = self._query_operands(q.shape[0])
         check(self.lib.vdb_flat_prepare_queries(ptr(q), q.shape[0], self.d, q.stride(0), ptr(q_hi), ptr(q_lo),
                                                 _stream(self.dev)), "vdb_flat_prepare_queries")
@@ -264,7 +277,7 @@ class Reranker:
         self.metric = metric
         base = to_device_f32(vectors, self.dev)
         if metric == "cosine":
-            normalize_rows_(base)
+            base = normalized_rows(base)
         self.n, self.d = base.shape
         self.base = pad_cols(base)
 
@@ -276,7 +289,7 @@ class Reranker:
         nq, c = cand.shape
         with torch.cuda.device(self.dev):
             if self.metric == "cosine":
-                normalize_rows_(q)
+                q = normalized_rows(q)
             qp = pad_cols(q)
             out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
             out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
@@ -284,6 +297,56 @@ class Reranker:
                                            ptr(cand), nq, c, ptr(qp), qp.stride(0), k, flags, pad_value,
                                            ptr(out_d), ptr(out_i), _stream(self.dev)), "vdb_rerank_topk")
         return out_d, out_i
+
+
+def kmeans_sample(vectors, nlist: int, seed: int = 1234, max_points_per_centroid: int = 256) -> Tuple[np.ndarray, np.ndarray]:
+    """(training rows, initial-centroid rows within them), both sorted: at most ``max_points_per_centroid * nlist``
+    rows drawn without replacement from ``RandomState(seed)``, then ``nlist`` distinct rows of the sample as the
+    starting centroids.  ``oracle.kmeans_lloyd`` restates exactly this draw order."""
+    n = int(vectors.shape[0])
+    rng = np.random.RandomState(seed)
+    limit = max_points_per_centroid * nlist
+    rows = np.sort(rng.choice(n, limit, replace=False)) if n > limit else np.arange(n)
+    init = np.sort(rng.permutation(rows.shape[0])[:nlist])
+    return rows, init
+
+
+def kmeans_step(sample: torch.Tensor, cent: torch.Tensor, spherical: bool, batch: int = 1 << 18) -> Tuple[torch.Tensor, np.ndarray]:
+    """One Lloyd iteration on the device: assignment = the flat scan kernel with base := centroids, k := 1
+    (L2, or inner product when ``spherical``), ``vdb_kmeans_accumulate`` for the sums, empty clusters re-seeded
+    by splitting the most populated one (FAISS does the same), spherical centroids re-normalised.
+    Returns (new centroids [nlist, d] on the device, cluster sizes before the split)."""
+    lib = _lib.load()
+    dev = sample.device
+    nlist, d = cent.shape
+    ns = sample.shape[0]
+    quant = FlatShard(cent, "ip" if spherical else "l2", dev)
+    sums = torch.zeros((nlist, d), dtype=torch.float32, device=dev)
+    counts = torch.zeros(nlist, dtype=torch.int32, device=dev)
+    for s in range(0, ns, batch):
+        blk = sample[s:s + batch]
+        _, idx = quant.search(blk, 1)
+        check(lib.vdb_kmeans_accumulate(ptr(blk), blk.shape[0], d, blk.stride(0), ptr(idx), nlist, ptr(sums),
+                                        ptr(counts), _stream(dev)), "vdb_kmeans_accumulate")
+    del quant
+    cnt_host = counts.cpu().numpy().astype(np.int64)
+    sizes = cnt_host.copy()
+    new = sums / counts.clamp(min=1).to(torch.float32)[:, None]
+    empty = np.nonzero(cnt_host == 0)[0]
+    if empty.size:
+        new_host = new.cpu().numpy()
+        for e in empty.tolist():
+            big = int(np.argmax(cnt_host))
+            eps = 1.0 / 1024.0
+            sign = np.where(np.arange(d) % 2 == 0, 1.0 + eps, 1.0 - eps).astype(np.float32)
+            new_host[e] = new_host[big] * sign
+            new_host[big] = new_host[big] * (2.0 - sign)
+            cnt_host[e] = cnt_host[big] // 2
+            cnt_host[big] -= cnt_host[e]
+        new = torch.from_numpy(new_host).to(dev)
+    if spherical:
+        new = normalized_rows(new)
+    return new, sizes
 
 
 def kmeans_train(vectors, nlist: int, metric: str = "l2", device=None, niter: int = 10, seed: int = 1234,
@@ -295,55 +358,21 @@ def kmeans_train(vectors, nlist: int, metric: str = "l2", device=None, niter: in
     training points sampled without replacement, ``niter`` iterations, random distinct rows as
     initial centroids, empty clusters re-seeded by splitting the most populated one.  l2: nearest
     centroid by L2; ip / cosine: spherical k-means (assignment by inner product, centroids
-    re-normalised).  FAISS's RNG stream is not reproduced (parity unpinned).
-    Assignment = the flat scan kernel with base := centroids, k := 1."""
-    lib = _lib.load()
+    re-normalised).  FAISS's RNG stream is not reproduced (parity unpinned vs FAISS, see DESIGN.md);
+    the recipe itself is pinned by ``oracle.kmeans_lloyd`` (same sample, same start, fp64)."""
     dev = _require_cuda(device)
-    n, d = int(vectors.shape[0]), int(vectors.shape[1])
+    n = int(vectors.shape[0])
     if n < nlist:
         raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({nlist})")
-    rng = np.random.RandomState(seed)
-    limit = max_points_per_centroid * nlist
-    if n > limit:
-        rows = np.sort(rng.choice(n, limit, replace=False))
-        sample_host = np.ascontiguousarray(vectors[rows], dtype=np.float32)
-    else:
-        sample_host = vectors
+    rows, init = kmeans_sample(vectors, nlist, seed, max_points_per_centroid)
+    sample_host = vectors if rows.shape[0] == n else np.ascontiguousarray(vectors[rows], dtype=np.float32)
     with torch.cuda.device(dev):
         sample = to_device_f32(sample_host, dev)
         if metric == "cosine":
-            normalize_rows_(sample)
-        ns = sample.shape[0]
-        init = torch.from_numpy(np.sort(rng.permutation(ns)[:nlist])).to(dev)
-        cent = sample[init].clone()
-        qmetric = "l2" if metric == "l2" else "ip"
+            sample = normalized_rows(sample)
+        cent = sample[torch.from_numpy(init).to(dev)].clone()
         for _ in range(max(niter, 0)):
-            quant = FlatShard(cent, qmetric, dev)
-            sums = torch.zeros((nlist, d), dtype=torch.float32, device=dev)
-            counts = torch.zeros(nlist, dtype=torch.int32, device=dev)
-            for s in range(0, ns, batch):
-                blk = sample[s:s + batch]
-                _, idx = quant.search(blk.clone(), 1)
-                check(lib.vdb_kmeans_accumulate(ptr(blk), blk.shape[0], d, blk.stride(0), ptr(idx), nlist, ptr(sums),
-                                                ptr(counts), _stream(dev)), "vdb_kmeans_accumulate")
-            del quant
-            cnt_host = counts.cpu().numpy().astype(np.int64)
-            new = sums / counts.clamp(min=1).to(torch.float32)[:, None]
-            empty = np.nonzero(cnt_host == 0)[0]
-            if empty.size:                                   # split the biggest clusters (FAISS does the same)
-                new_host = new.cpu().numpy()
-                for j, e in enumerate(empty.tolist()):
-                    big = int(np.argmax(cnt_host))
-                    eps = 1.0 / 1024.0
-                    sign = np.where(np.arange(d) % 2 == 0, 1.0 + eps, 1.0 - eps).astype(np.float32)
-                    new_host[e] = new_host[big] * sign
-                    new_host[big] = new_host[big] * (2.0 - sign)
-                    cnt_host[e] = cnt_host[big] // 2
-                    cnt_host[big] -= cnt_host[e]
-                new = torch.from_numpy(new_host).to(dev)
-            if qmetric == "ip":
-                normalize_rows_(new)
-            cent = new
+            cent, _ = kmeans_step(sample, cent, metric != "l2", batch)
         torch.cuda.current_stream(dev).synchronize()
         return cent.cpu().numpy()
 
@@ -360,7 +389,7 @@ class IVFShard:
         self.id_offset = int(id_offset)
         base = to_device_f32(vectors, self.dev)
         if metric == "cosine":
-            normalize_rows_(base)
+            base = normalized_rows(base)
         self.n, self.d = base.shape
         cent = to_device_f32(centroids, self.dev)
         self.nlist = cent.shape[0]
@@ -370,7 +399,7 @@ class IVFShard:
         with torch.cuda.device(self.dev):
             assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
             for s in range(0, self.n, assign_batch):
-                _, idx = self.quantizer.search(base[s:s + assign_batch].clone(), 1)
+                _, idx = self.quantizer.search(base[s:s + assign_batch], 1)
                 assign[s:s + assign_batch] = idx[:, 0].to(torch.int32)
             self.assign = assign
             counts = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
@@ -419,8 +448,8 @@ class IVFShard:
         nprobe = max(1, min(int(nprobe), self.nlist))
         with torch.cuda.device(self.dev):
             if self.metric == "cosine":
-                normalize_rows_(q)
-            _, probes = self.quantizer.search(q.clone(), nprobe)
+                q = normalized_rows(q)
+            _, probes = self.quantizer.search(q, nprobe)
             out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
             out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
             check(self.lib.vdb_ivf_scan_topk(metric_code(self.metric), ptr(self.list_vecs), ptr(self.list_ids),
