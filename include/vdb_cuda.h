@@ -102,13 +102,20 @@ int vdb_flat_topk(int metric, const float* hi, const float* lo, const float* nor
                   float* out_d, int64_t* out_i,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Size of the persistent tcgen05 grid (clusters of 1 or 2 CTAs) the scan launches for dimension d on the current
+ * device: min(SMs / cluster size, clusters the occupancy calculator reports as co-resident).  The pool hand-over
+ * between work items needs every cluster of the grid resident at once, so the grid never exceeds this. */
+int vdb_flat_grid_clusters(int impl, int d, int* out);
+
 /* Debug / test hook: dense key matrix of the tcgen05 contraction for a small problem,
  * keys [nq_pad, n_pad] fp32 (n_pad, nq_pad as above).  impl: VDB_IMPL_TCGEN05 / _1CTA / SIMT. */
 int vdb_flat_dense_keys(const float* hi, const float* lo, const float* norms, int64_t n, int d,
                         const float* q_hi, const float* q_lo, int64_t nq, int impl,
                         float* keys, void* stream);
 
-/* Bring-up knob for kernel timing experiments (results are WRONG for mode != 0): 2 = filter
+/* The knobs below (debug mode, seeding override, timing log) are PER HOST THREAD: set by one thread, they affect
+ * only the calls that thread makes.
+ * Bring-up knob for kernel timing experiments (results are WRONG for mode != 0): 2 = filter
  * but never append a candidate, 3 = do not read the accumulators at all (contraction pipeline
  * only), 5 = start from the bounds the previous call left in the workspace (perfect warm start).
  * Returns the previous mode. */

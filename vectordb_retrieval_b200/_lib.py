@@ -38,6 +38,7 @@ SIGNATURES = {
     "vdb_flat_topk_workspace_bytes": (_sz, [_i64, _i32]),
     "vdb_flat_topk": (_i32, [_i32, _p, _p, _p, _i64, _i32, _i64, _p, _p, _i64, _i32, _i32, _f32, _i32,
                              _p, _p, _p, _sz, _p]),
+    "vdb_flat_grid_clusters": (_i32, [_i32, _i32, C.POINTER(C.c_int)]),
     "vdb_flat_dense_keys": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _i64, _i32, _p, _p]),
     "vdb_set_debug_mode": (_i32, [_i32]),
     "vdb_debug_read_prof": (_i32, [C.POINTER(C.c_uint64)]),

@@ -135,6 +135,8 @@ class FaissFactoryIndexer(BaseIndexer):
     (modular.py:238-262) - the normalisation itself runs on the device."""
 
     _RESERVED_PARAM_KEYS = {"index_key", "index_type", "device", "devices"}
+    _TRAIN_PARAM_KEYS = ("niter", "seed", "max_points_per_centroid")      # shape the centroids: must be set BEFORE train()
+    _RUNTIME_PARAM_KEYS = ("nprobe",)                                      # search-time attributes (modular.py:269-275)
 
     def __init__(self, name: str, dimension: int, metric: str = "l2", index_key: str = "Flat", **kwargs: Any) -> None:
         from ..indexes import _IVF_FLAT
@@ -158,14 +160,18 @@ class FaissFactoryIndexer(BaseIndexer):
         elif self.metric == "ip":
             kind = "ip"
             meta["faiss_metric"] = "ip"
-        index = index_factory(self.dimension, self.index_key, kind, device=self.params.get("device"), normalize=normalize)
+        train_kwargs = {key: self.params[key] for key in self._TRAIN_PARAM_KEYS
+                        if key in self.params and self.index_key.strip() != "Flat"}
+        index = index_factory(self.dimension, self.index_key, kind, device=self.params.get("device"), normalize=normalize,
+                              **train_kwargs)
+        meta.update(train_kwargs)
         if not index.is_trained:
             index.train(vectors)
         index.add(vectors)
-        for key, value in self.params.items():          # runtime knobs such as nprobe (modular.py:269-275)
-            if key not in self._RESERVED_PARAM_KEYS and hasattr(index, key):
-                setattr(index, key, value)
-                meta[key] = value
+        for key in self._RUNTIME_PARAM_KEYS:            # runtime knobs such as nprobe (modular.py:269-275)
+            if key in self.params and hasattr(index, key):
+                setattr(index, key, self.params[key])
+                meta[key] = self.params[key]
         return IndexArtifact(kind="faiss", data=index, metadata=meta)
 
 

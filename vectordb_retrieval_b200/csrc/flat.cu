@@ -54,6 +54,12 @@ static int max_pools(int64_t nq, int sm) {
   return std::min(std::max(a, b), 2 * sm) + 2;
 }
 
+// Clusters of the persistent tcgen05 grid that can be CO-RESIDENT on the current device.  The lineage hand-over
+// (flat_tc.cuh) makes a running cluster wait for an item owned by another cluster of the same grid, which is only
+// deadlock-free when every cluster of the grid is on an SM at the same time; the raw SM count over-states that when
+// SMs are shared or withheld (MPS, green contexts, unpaired SMs), so the occupancy calculator has the last word.
+static int coresident_clusters(int cta_group, bool a_resident, int sm);
+
 static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int kpad, int sm) {
   FlatPlan p{};
   if (impl == VDB_IMPL_SIMT) {
@@ -61,7 +67,8 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int kpad, int sm)
     p.n_qtiles = static_cast<int>((nq + 63) / 64);
   } else {
     p.cta_group = impl == VDB_IMPL_TCGEN05_1CTA ? 1 : 2;
-    p.tile_rows = 128 * p.cta_group; p.slots = sm / p.cta_group;
+    p.tile_rows = 128 * p.cta_group;
+    p.slots = std::max(1, std::min(sm / p.cta_group, coresident_clusters(p.cta_group, kpad / 32 <= tc::kMaxResidentKb, sm)));
     p.n_qtiles = static_cast<int>((nq + p.tile_rows - 1) / p.tile_rows);
   }
   p.n_tiles = static_cast<int>(n_pad / p.tile_rows);
@@ -81,7 +88,9 @@ static FlatPlan make_plan(int impl, int64_t nq, int64_t n_pad, int kpad, int sm)
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
-static int g_debug_mode = 0;
+// Bring-up / measurement knobs are PER THREAD: a debug mode or a seeding override set by one host thread (a test, a
+// profiling script) cannot change the results of an index another thread is searching.
+static thread_local int g_debug_mode = 0;
 
 // Seeded bounds (tcgen05 path, large shards).  A lineage that starts with an infinite bound accepts
 // every key until its pool has seen ~k'/p rows for a hit rate p - roughly the first 200k rows of
@@ -94,8 +103,8 @@ static int g_debug_mode = 0;
 // reset and re-scanned from an infinite bound by a third launch that skips every query tile
 // without such a query (normally all of them).  S is capped so that r * N / S >= margin * k':
 // for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) ~ 1e-10.
-static int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
-static int g_pre_rank = 16;      // r (1..32)
+static thread_local int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
+static thread_local int g_pre_rank = 16;      // r (1..32)
 __device__ unsigned long long g_redo_queries;
 
 struct PrePlan {
@@ -106,10 +115,10 @@ struct PrePlan {
 
 // bench.py's roofline leg: scan-kernel durations measured with CUDA events on the launching stream
 constexpr int kTimingSlots = 512;
-static bool g_timing_on = false;
-static int g_timing_n = 0;
-static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
-static bool g_ev_made = false;
+static thread_local bool g_timing_on = false;
+static thread_local int g_timing_n = 0;
+static thread_local cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
+static thread_local bool g_ev_made = false;
 
 // --------------------------------------------------------------------------------------------
 __global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int* handover,
@@ -540,12 +549,12 @@ static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUten
                      const FlatScanParams& P, int clusters, cudaStream_t stream) {
   auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE, SEED, HAM>;
   constexpr int smem = tc::smem_bytes<ARES>();
-  static bool configured[64] = {};
+  static int configured[64] = {};     // per device; the attribute call is idempotent, so a race only repeats it
   int dev = 0;
   VDB_CHECK_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
+  if (!__atomic_load_n(&configured[dev & 63], __ATOMIC_ACQUIRE)) {
     VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[dev & 63] = true;
+    __atomic_store_n(&configured[dev & 63], 1, __ATOMIC_RELEASE);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
@@ -561,6 +570,37 @@ static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUten
   cfg.numAttrs = 1;
   VDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mqh, mql, mbh, mbl, P));
   return 0;
+}
+
+template <int CG, bool ARES>
+static int query_coresident(int sm) {
+  auto kern = flat_scan_tc_kernel<CG, ARES, 128, false>;
+  constexpr int smem = tc::smem_bytes<ARES>();
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return sm / CG; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sm / CG * CG);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); return sm / CG; }
+  return n;
+}
+
+static int coresident_clusters(int cta_group, bool a_resident, int sm) {
+  // cached per (thread, device, variant): the answer is a property of the device / context partition
+  thread_local int cache[64][4] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return sm / cta_group; }
+  int& slot = cache[dev & 63][(cta_group == 2 ? 2 : 0) + (a_resident ? 1 : 0)];
+  if (slot == 0) {
+    slot = cta_group == 2 ? (a_resident ? query_coresident<2, true>(sm) : query_coresident<2, false>(sm))
+                          : (a_resident ? query_coresident<1, true>(sm) : query_coresident<1, false>(sm));
+  }
+  return slot;
 }
 
 template <int KP>
@@ -841,6 +881,16 @@ int vdb_set_debug_mode(int mode) {
   const int old = g_debug_mode;
   g_debug_mode = mode;
   return old;
+}
+
+int vdb_flat_grid_clusters(int impl, int d, int* out) {
+  int sm = 0;
+  if (vdb_sm_count(&sm)) return 1;
+  if (impl == VDB_IMPL_AUTO) impl = VDB_IMPL_TCGEN05;
+  VDB_REQUIRE((impl == VDB_IMPL_TCGEN05 || impl == VDB_IMPL_TCGEN05_1CTA) && d > 0 && out != nullptr, "vdb_flat_grid_clusters: bad arguments");
+  const int cg = impl == VDB_IMPL_TCGEN05_1CTA ? 1 : 2;
+  *out = std::max(1, std::min(sm / cg, coresident_clusters(cg, vdb_flat_kpad(d) / 32 <= tc::kMaxResidentKb, sm)));
+  return 0;
 }
 
 int vdb_debug_read_prof(uint64_t* out8) {

@@ -70,7 +70,9 @@ struct WarpTopK {
   // every lane of the warp calls; `valid` lanes offer one (key,row) each
   __device__ __forceinline__ void push(bool valid, float key, uint32_t row, int lane) {
     if (cnt > CAP - 32) compact(lane);
-    const bool pass = valid && key < thr;
+    // `<=`: a key equal to the bound may still belong to the best KP by (key, row) order - the compaction
+    // keeps the lowest rows of a tie group - so the result never depends on the order rows are met in
+    const bool pass = valid && key <= thr;
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (pass) pool[cnt + __popc(m & ((1u << lane) - 1u))] = pack_key(key, row);
     cnt += __popc(m);

@@ -14,6 +14,8 @@ from . import _lib
 from ._lib import METRIC_IP, METRIC_L2, check, ptr
 
 FLT_MAX = float(np.finfo(np.float32).max)
+MAX_FLAT_K = 504        # vdb_flat_topk keeps k' >= k + 8 candidates in pools of at most 512 (common.cuh keep_for_k)
+MAX_LIST_K = 512        # IVF scan, rerank and merge kernels
 
 
 def _require_cuda(device) -> torch.device:
@@ -180,7 +182,7 @@ class FlatShard:
         if ws is None:
             nbytes = self.lib.vdb_flat_topk_workspace_bytes(nq, k)
             if nbytes == 0:
-                raise RuntimeError(f"k={k} is not supported by the flat search (1..504)")
+                raise RuntimeError(f"k={k} is not supported by the flat search (1..{MAX_FLAT_K})")
             self._ws.clear()  # one live workspace per shard
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
             self._ws[key] = ws
@@ -446,6 +448,9 @@ class IVFShard:
                scanned: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         nq = q.shape[0]
         nprobe = max(1, min(int(nprobe), self.nlist))
+        if nprobe > MAX_FLAT_K:
+            raise RuntimeError(f"nprobe={nprobe} is not supported: the coarse quantiser selects at most {MAX_FLAT_K} lists "
+                               f"per query (flat top-k limit); use nprobe <= {MAX_FLAT_K}")
         with torch.cuda.device(self.dev):
             if self.metric == "cosine":
                 q = normalized_rows(q)
