@@ -256,12 +256,12 @@ def _measure(label, index, algo, q_dev, q_host_np, args, lib, dev, world, rank, 
     flush_buf = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev) if flush else None
     # (results are held like in the timed loops: with the previous step's arrays still alive the second
     # call needs a second set of pinned host blocks, and a fresh cudaHostAlloc costs 10-30 ms once)
+    if sampler is not None:          # started before the warm-up: nvidia-smi needs ~0.3 s before its first sample
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         d_dev, i_dev = index.search(q_dev, TOPK)
         d_host, i_host = algo.batch_search(q_host_np, TOPK)
     barrier()
-    if sampler is not None:
-        sampler.start()
     lib.vdb_flat_timing_enable(1)
     launches0 = lib.vdb_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -672,6 +672,7 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
   FlatScanParams P{};
   P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
   P.n_chunks = plan.n_chunks; P.n_pools = plan.n_pools; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.kslices = (d + 7) / 8;
   P.handover = reinterpret_cast<int*>(w + off_hand);
   P.trash = reinterpret_cast<uint64_t*>(w + off_trash);
   P.thr = reinterpret_cast<uint32_t*>(w);
@@ -1092,6 +1093,7 @@ int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_
   FlatScanParams P{};
   P.norms = norms; P.nq = nq; P.n_tiles = plan.n_tiles; P.tiles_per_chunk = plan.tiles_per_chunk;
   P.n_chunks = plan.n_chunks; P.n_pools = plan.n_chunks; P.n_qtiles = plan.n_qtiles; P.kb = kpad / 32;
+  P.kslices = 4 * P.kb;
   P.tile_stride = 1; P.ham_nbits = nbits; P.ham_bound = T; P.ham_list = list; P.ham_cnt = lcnt; P.ham_cap = cap;
   CUtensorMap mq, mb;
   if (make_operand_map(&mq, static_cast<const float*>(q_bf16), nq_pad, kpad) ||

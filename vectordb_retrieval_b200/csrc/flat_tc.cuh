@@ -49,6 +49,7 @@ struct FlatScanParams {
   uint64_t* trash;      // tcgen05 kernel: [nq_pad] write-only slots for keys that miss the bound
   int* handover;        // tcgen05 kernel: [n_qtiles][n_pools] hand-over counters between the chunks of a lineage
   int kb;               // k-blocks of 32 (kpad / 32)
+  int kslices;          // K = 8 MMA slices that hold data: ceil(d / 8) (<= 4 * kb); the zero slices of the last k-block are not issued
   uint64_t* pools;      // [nq_pad][n_pools][pool_cap(KP)]
   int* pool_cnt;        // [nq_pad][n_pools]
   uint32_t* thr;        // [nq_pad] ordered-uint running bounds shared by all CTAs
@@ -236,19 +237,22 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                                                : smem_u32(st + 3 * tc::kBlockBytes);
               const uint64_t da_hi = make_sw128_kmajor_desc(a_hi), da_lo = make_sw128_kmajor_desc(a_lo);
               const uint64_t db_hi = make_sw128_kmajor_desc(b_hi), db_lo = make_sw128_kmajor_desc(b_lo);
+              // slices of this k-block that hold data (d = 50: the second block has 3 of 4 - the padding
+              // columns 56..63 are zero in both operands, so skipping their MMAs changes nothing but the time)
+              const int ns = min(4, P.kslices - kbi * 4);
               if constexpr (kHam != 0) {   // bf16 codes: 64 elements per 128-byte block, K = 16 per MMA
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC_BF16, (kbi | k) != 0);
               } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // 4 x K=8 per 32-wide block: +32 bytes inside the swizzle atom
-                umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC, (kbi | k) != 0);
+                if (k < ns) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_hi + 2 * k, IDESC, (kbi | k) != 0);
               }
               if constexpr (!kSeed && kHam == 0) {   // the seeding pre-pass only guesses: plain TF32 keys (1e-3 relative) do
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
+                for (int k = 0; k < 4; ++k) if (k < ns) umma_tf32<kCtaGroup>(tmem_d, da_hi + 2 * k, db_lo + 2 * k, IDESC, 1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32<kCtaGroup>(tmem_d, da_lo + 2 * k, db_hi + 2 * k, IDESC, 1);
+                for (int k = 0; k < 4; ++k) if (k < ns) umma_tf32<kCtaGroup>(tmem_d, da_lo + 2 * k, db_hi + 2 * k, IDESC, 1);
               }
               umma_commit<kCtaGroup>(empty_bar + stage);
               if (kbi == P.kb - 1) umma_commit<kCtaGroup>(tmem_full_bar + buf);

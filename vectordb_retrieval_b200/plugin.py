@@ -57,7 +57,13 @@ def _stub_missing_modules() -> None:
         mpl.use = lambda *a, **k: None
         plt = types.ModuleType("matplotlib.pyplot")
         plt.subplots = lambda *a, **k: (inert, inert)
-        plt.__getattr__ = lambda name: inert           # module-level __getattr__ (PEP 562): figure, savefig, close, ...
+
+        def _plt_attr(name: str):                      # module-level __getattr__ (PEP 562): figure, savefig, close, ...
+            if name.startswith("__"):                  # inspect / importlib probe __file__, __path__, __spec__: absent
+                raise AttributeError(name)
+            return inert
+
+        plt.__getattr__ = _plt_attr
         mpl.pyplot = plt
         sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
 
