@@ -304,7 +304,7 @@ class Reranker:
 def kmeans_sample(vectors, nlist: int, seed: int = 1234, max_points_per_centroid: int = 256) -> Tuple[np.ndarray, np.ndarray]:
     """(training rows, initial-centroid rows within them), both sorted: at most ``max_points_per_centroid * nlist``
     rows drawn without replacement from ``RandomState(seed)``, then ``nlist`` distinct rows of the sample as the
-    starting centroids.  ``oracle.kmeans_lloyd`` restates exactly this draw order."""
+    starting centroids.  the fp64 Lloyd restatement under oracle/ repeats exactly this draw order."""
     n = int(vectors.shape[0])
     rng = np.random.RandomState(seed)
     limit = max_points_per_centroid * nlist
@@ -361,7 +361,7 @@ def kmeans_train(vectors, nlist: int, metric: str = "l2", device=None, niter: in
     initial centroids, empty clusters re-seeded by splitting the most populated one.  l2: nearest
     centroid by L2; ip / cosine: spherical k-means (assignment by inner product, centroids
     re-normalised).  FAISS's RNG stream is not reproduced (parity unpinned vs FAISS, see DESIGN.md);
-    the recipe itself is pinned by ``oracle.kmeans_lloyd`` (same sample, same start, fp64)."""
+    the recipe itself is pinned by the fp64 Lloyd restatement under oracle/ (same sample, same start)."""
     dev = _require_cuda(device)
     n = int(vectors.shape[0])
     if n < nlist:
