@@ -167,6 +167,24 @@ def test_rerank_matches_reference_golden_and_oracle(eng, metric):
         np.testing.assert_allclose(D1.cpu().numpy()[np.isfinite(ref[0])], 1.0 + ref[0][np.isfinite(ref[0])], atol=2e-6)
 
 
+@pytest.mark.parametrize("c,k", [(40, 10), (800, 100), (1600, 100), (3000, 200), (1100, 500)])
+def test_rerank_launch_shapes_match_oracle(eng, c, k):
+    """1, 2, 4 and 8 warps per query (about 512 candidates per warp; several queries share a CTA below 8):
+    every shape must give the oracle's rerank, including short and empty candidate rows."""
+    from vectordb_retrieval_b200 import _lib
+    base, q = _data(20000, 50, 77, seed=c)
+    rng = np.random.RandomState(c + 1)
+    cand = np.stack([rng.permutation(20000)[:c] for _ in range(77)]).astype(np.int64)
+    cand[5, c // 2:] = -1
+    cand[9, :] = -1
+    for metric, flags in (("l2", _lib.OUT_SQRT), ("ip", _lib.OUT_NEGATE)):
+        rr = eng.Reranker(base, metric, "cuda")
+        D, I = rr.search(torch.from_numpy(q).cuda(), torch.from_numpy(cand).cuda(), k, flags, float("inf"))
+        ref = oracle.rerank_search(base, cand, q, k, metric)
+        _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if metric == "l2" else 1e-5)
+        assert (I.cpu().numpy()[9] == -1).all() and np.isinf(D.cpu().numpy()[9]).all()
+
+
 @pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
 def test_ivf_scan_matches_oracle_given_same_centroids(eng, metric):
     base, q = _data(30000, 50, 200, seed=31)
@@ -181,7 +199,7 @@ def test_ivf_scan_matches_oracle_given_same_centroids(eng, metric):
     got_assign = ivf.assign.cpu().numpy()
     assert (got_assign == assign).mean() > 0.9999   # fp ties between two centroids are the only freedom
     assert int(ivf.counts.sum().item()) == 30000
-    for nprobe in (1, 8, 64):
+    for nprobe in (1, 2, 4, 8, 64):           # 1 / 2 / 4 / 8 warps per query (about 512 expected rows per warp)
         scanned = torch.zeros(1, dtype=torch.int64, device="cuda")
         D, I = ivf.search(torch.from_numpy(q.copy()).cuda(), 100, nprobe, 0,
                           oracle.FLT_MAX if m == "l2" else -oracle.FLT_MAX, scanned)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "vdb_ivf_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _i32, _p, _p, _p, _p]),
     "vdb_ivf_scan_topk": (_i32, [_i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
                                  _p, _p, _p, _p]),
+    "vdb_ivf_scan_topk_ex": (_i32, [_i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
+                                    _p, _p, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

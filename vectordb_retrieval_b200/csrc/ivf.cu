@@ -51,22 +51,35 @@ __global__ void kmeans_accumulate_kernel(const float* __restrict__ x, int64_t n,
   if (lane == 0) atomicAdd(counts + l, 1);
 }
 
-template <int KP, int W>
-__global__ void __launch_bounds__(W * 32, 1024 / (W * 32))
+// W warps serve one query and a CTA of TW warps holds TW / W queries: one query per 8 warps (W = TW) suits long
+// scans; at nprobe 1-8 over ~300-row lists that leaves a warp one or two 32-row blocks, no pool ever fills and the
+// per-query fixed work (staging the query, two barriers, the merge by one warp) dominates - 0.30 of the HBM rate at
+// nprobe 1.  The host picks W from the expected rows per query (~512 rows per warp).
+template <int KP, int W, int TW>
+__global__ void __launch_bounds__(TW * 32, 1024 / (TW * 32))
 ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __restrict__ ids,
                 const int32_t* __restrict__ blk_off, int nlist, int d4, const int64_t* __restrict__ probes, int nprobe,
-                const float* __restrict__ qmat, int64_t ld_q, int d, int k, int flags, float pad_value, int64_t id_offset,
-                float* __restrict__ out_d, int64_t* __restrict__ out_i, unsigned long long* scanned) {
+                const float* __restrict__ qmat, int64_t ld_q, int64_t nq, int d, int k, int flags, float pad_value,
+                int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i, unsigned long long* scanned) {
   constexpr int CAP = pool_cap(KP);
+  constexpr int QPC = TW / W;                 // queries per CTA
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
-  int* cnts = reinterpret_cast<int*>(pools + W * CAP);
-  float4* qs = reinterpret_cast<float4*>(cnts + W);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q = blockIdx.x;
+  uint64_t* pools_all = reinterpret_cast<uint64_t*>(smem_dyn);
+  int* cnts_all = reinterpret_cast<int*>(pools_all + TW * CAP);
+  float* thr_all = reinterpret_cast<float*>(cnts_all + TW);
   const int d4p = (d4 + 7) & ~7;
-  for (int j = threadIdx.x; j < d4p * 4; j += W * 32) reinterpret_cast<float*>(qs)[j] = j < d ? qmat[q * ld_q + j] : 0.f;
-  __syncthreads();
+  float4* qs_all = reinterpret_cast<float4*>(thr_all + TW);      // TW is a multiple of 4: stays 16-byte aligned
+  const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp_cta / W, warp = warp_cta % W;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * QPC + group;
+  if (q >= nq) return;                        // whole groups leave together: the group barriers below stay balanced
+  uint64_t* pools = pools_all + group * W * CAP;
+  int* cnts = cnts_all + group * W;
+  float* thr_s = thr_all + group * W;
+  float4* qs = qs_all + group * d4p;
+  const int bar_id = 1 + group;
+  for (int j = warp * 32 + lane; j < d4p * 4; j += W * 32) reinterpret_cast<float*>(qs)[j] = j < d ? qmat[q * ld_q + j] : 0.f;
+  group_sync<W * 32>(bar_id);
   WarpTopK<KP> sel;
   sel.init(pools + warp * CAP);
   unsigned rows_seen = 0;
@@ -107,24 +120,33 @@ ivf_scan_kernel(int metric, const float4* __restrict__ vecs, const int32_t* __re
     }
   }
   if (scanned != nullptr && lane == 0 && rows_seen) atomicAdd(scanned, static_cast<unsigned long long>(rows_seen));
-  cta_write_topk<KP, W>(sel, pools, cnts, warp, lane, metric, k, flags, pad_value, id_offset, out_d + q * k, out_i + q * k);
+  cta_write_topk<KP, W>(sel, pools, cnts, thr_s, warp, lane, bar_id, metric, k, flags, pad_value, id_offset, out_d + q * k,
+                        out_i + q * k);
 }
 
-template <int KP, int W>
+template <int KP, int W, int TW>
 static int launch_scan(int metric, const float* vecs, const int32_t* ids, const int32_t* blk_off, int nlist, int d,
                        const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k, int flags,
                        float pad_value, int64_t id_offset, float* out_d, int64_t* out_i, int64_t* scanned,
                        cudaStream_t stream) {
   const int d4 = (d + 3) / 4;
-  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>((d4 + 7) & ~7) * 16;
-  auto kern = ivf_scan_kernel<KP, W>;
+  constexpr int QPC = TW / W;
+  const size_t smem = static_cast<size_t>(TW) * pool_cap(KP) * 8 + TW * 8 + static_cast<size_t>(QPC) * ((d4 + 7) & ~7) * 16;
+  auto kern = ivf_scan_kernel<KP, W, TW>;
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(
-      metric, reinterpret_cast<const float4*>(vecs), ids, blk_off, nlist, d4, probes, nprobe, q, ld_q, d, k, flags,
+  kern<<<static_cast<unsigned>((nq + QPC - 1) / QPC), TW * 32, smem, stream>>>(
+      metric, reinterpret_cast<const float4*>(vecs), ids, blk_off, nlist, d4, probes, nprobe, q, ld_q, nq, d, k, flags,
       pad_value, id_offset, out_d, out_i, reinterpret_cast<unsigned long long*>(scanned));
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// warps per query for an expected number of scanned rows per query: about 512 rows per warp, a power of two <= tw
+static int warps_for_rows(int64_t rows, int tw) {
+  int w = 1;
+  while (w < tw && static_cast<int64_t>(w) * 512 < rows) w *= 2;
+  return w;
 }
 
 }  // namespace vdb
@@ -163,26 +185,45 @@ int vdb_ivf_fill(const float* x, int64_t n, int d, int64_t ld, const int32_t* as
   return 0;
 }
 
-int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_ids, const int32_t* blk_off, int nlist,
-                      int d, const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k,
-                      int flags, float pad_value, int64_t id_offset, float* out_d, int64_t* out_i,
-                      int64_t* scanned_rows, void* stream) {
+int vdb_ivf_scan_topk_ex(int metric, const float* list_vecs, const int32_t* list_ids, const int32_t* blk_off, int nlist,
+                         int d, const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k,
+                         int flags, float pad_value, int64_t id_offset, float* out_d, int64_t* out_i,
+                         int64_t* scanned_rows, int64_t rows_per_query_hint, void* stream) {
   VDB_REQUIRE(metric == VDB_METRIC_L2 || metric == VDB_METRIC_IP, "vdb_ivf_scan_topk: bad metric %d", metric);
   VDB_REQUIRE(nq > 0 && d > 0 && nlist > 0 && nprobe >= 1 && ld_q >= d, "vdb_ivf_scan_topk: bad shape");
   VDB_REQUIRE((reinterpret_cast<uintptr_t>(list_vecs) & 15) == 0, "vdb_ivf_scan_topk: list_vecs must be 16-byte aligned");
   const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
   VDB_REQUIRE(k >= 1 && kp != 0, "vdb_ivf_scan_topk: k=%d unsupported (1..512)", k);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define VDB_GO(KP, W)                                                                                              \
-  return launch_scan<KP, W>(metric, list_vecs, list_ids, blk_off, nlist, d, probes, nprobe, q, ld_q, nq, k, flags, \
-                            pad_value, id_offset, out_d, out_i, scanned_rows, s)
-  switch (kp) {
-    case 32: VDB_GO(32, 8);
-    case 128: VDB_GO(128, 8);
-    case 256: VDB_GO(256, 8);
-    default: VDB_GO(512, 4);
+  const int tw = kp == 512 ? 4 : 8;
+  int w = rows_per_query_hint > 0 ? warps_for_rows(rows_per_query_hint, tw) : tw;
+  while (w < tw && static_cast<size_t>(tw / w) * (((d + 3) / 4 + 7) & ~7) * 16 > 64 * 1024) w *= 2;   // staged queries must fit shared memory
+#define VDB_GO(KP, W, TW)                                                                                              \
+  return launch_scan<KP, W, TW>(metric, list_vecs, list_ids, blk_off, nlist, d, probes, nprobe, q, ld_q, nq, k, flags, \
+                                pad_value, id_offset, out_d, out_i, scanned_rows, s)
+#define VDB_PICK(KP, TW)                        \
+  switch (w) {                                  \
+    case 1: VDB_GO(KP, 1, TW);                  \
+    case 2: VDB_GO(KP, 2, TW);                  \
+    case 4: VDB_GO(KP, 4, TW);                  \
+    default: VDB_GO(KP, TW, TW);                \
   }
+  switch (kp) {
+    case 32: VDB_PICK(32, 8)
+    case 128: VDB_PICK(128, 8)
+    case 256: VDB_PICK(256, 8)
+    default: VDB_PICK(512, 4)
+  }
+#undef VDB_PICK
 #undef VDB_GO
+}
+
+int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_ids, const int32_t* blk_off, int nlist,
+                      int d, const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k,
+                      int flags, float pad_value, int64_t id_offset, float* out_d, int64_t* out_i,
+                      int64_t* scanned_rows, void* stream) {
+  return vdb_ivf_scan_topk_ex(metric, list_vecs, list_ids, blk_off, nlist, d, probes, nprobe, q, ld_q, nq, k, flags, pad_value,
+                              id_offset, out_d, out_i, scanned_rows, 0, stream);
 }
 
 }  // extern "C"

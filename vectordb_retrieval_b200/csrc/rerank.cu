@@ -7,20 +7,33 @@
 
 namespace vdb {
 
-template <int KP, int W>
-__global__ void __launch_bounds__(W * 32)
+// W warps serve one query, a CTA of TW warps holds TW / W queries (see ivf.cu): with C = 800 candidates one query per
+// 8 warps gives a warp 100 candidates - no pool ever reaches its KP-th key, nothing is filtered, and the group's
+// merging warp sorts all 800 entries serially (7 x 256-element bitonic merges, ~40 us per query): 0.31 of the HBM rate.
+// About 512 candidates per warp keeps the pools filtering and the merge short.
+template <int KP, int W, int TW>
+__global__ void __launch_bounds__(TW * 32)
 rerank_topk_kernel(int metric, const float* __restrict__ base, int64_t n, int dpad, int64_t ld,
-                   const int64_t* __restrict__ cand, int c, const float* __restrict__ qmat, int64_t ld_q,
+                   const int64_t* __restrict__ cand, int64_t nq, int c, const float* __restrict__ qmat, int64_t ld_q,
                    int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
   constexpr int CAP = pool_cap(KP);
+  constexpr int QPC = TW / W;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint64_t* pools = reinterpret_cast<uint64_t*>(smem_dyn);
-  int* cnts = reinterpret_cast<int*>(pools + W * CAP);
-  float* qs = reinterpret_cast<float*>(cnts + W);   // W is a multiple of 4: stays 16-byte aligned
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q = blockIdx.x;
-  for (int j = threadIdx.x; j < dpad; j += W * 32) qs[j] = qmat[q * ld_q + j];
-  __syncthreads();
+  uint64_t* pools_all = reinterpret_cast<uint64_t*>(smem_dyn);
+  int* cnts_all = reinterpret_cast<int*>(pools_all + TW * CAP);
+  float* thr_all = reinterpret_cast<float*>(cnts_all + TW);
+  float* qs_all = thr_all + TW;                 // TW is a multiple of 4: stays 16-byte aligned
+  const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp_cta / W, warp = warp_cta % W;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * QPC + group;
+  if (q >= nq) return;                          // whole groups leave together
+  uint64_t* pools = pools_all + group * W * CAP;
+  int* cnts = cnts_all + group * W;
+  float* thr_s = thr_all + group * W;
+  float* qs = qs_all + group * dpad;
+  const int bar_id = 1 + group;
+  for (int j = warp * 32 + lane; j < dpad; j += W * 32) qs[j] = qmat[q * ld_q + j];
+  group_sync<W * 32>(bar_id);
   WarpTopK<KP> sel;
   sel.init(pools + warp * CAP);
   const int sub = lane >> 3, sl = lane & 7;
@@ -77,18 +90,19 @@ rerank_topk_kernel(int metric, const float* __restrict__ base, int64_t n, int dp
     }
     sel.push(my_valid, my_key, my_id, lane);
   }
-  cta_write_topk<KP, W>(sel, pools, cnts, warp, lane, metric, k, flags, pad_value, 0, out_d + q * k, out_i + q * k);
+  cta_write_topk<KP, W>(sel, pools, cnts, thr_s, warp, lane, bar_id, metric, k, flags, pad_value, 0, out_d + q * k, out_i + q * k);
 }
 
-template <int KP, int W>
+template <int KP, int W, int TW>
 static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int64_t ld, const int64_t* cand, int64_t nq,
                          int c, const float* q, int64_t ld_q, int k, int flags, float pad_value, float* out_d,
                          int64_t* out_i, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(W) * pool_cap(KP) * 8 + W * 4 + static_cast<size_t>(dpad) * 4;
-  auto kern = rerank_topk_kernel<KP, W>;
+  constexpr int QPC = TW / W;
+  const size_t smem = static_cast<size_t>(TW) * pool_cap(KP) * 8 + TW * 8 + static_cast<size_t>(QPC) * dpad * 4;
+  auto kern = rerank_topk_kernel<KP, W, TW>;
   if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<static_cast<unsigned>(nq), W * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, c, q, ld_q, k, flags,
-                                                             pad_value, out_d, out_i);
+  kern<<<static_cast<unsigned>((nq + QPC - 1) / QPC), TW * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k,
+                                                                             flags, pad_value, out_d, out_i);
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -113,10 +127,25 @@ extern "C" int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, 
   const int kp = k <= 32 ? 32 : k <= 128 ? 128 : k <= 256 ? 256 : k <= 512 ? 512 : 0;
   VDB_REQUIRE(k >= 1 && kp != 0, "vdb_rerank_topk: k=%d unsupported (1..512)", k);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (kp) {
-    case 32: return launch_rerank<32, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
-    case 128: return launch_rerank<128, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
-    case 256: return launch_rerank<256, 8>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
-    default: return launch_rerank<512, 4>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);
+  const int tw = kp == 512 ? 4 : 8;
+  int w = 1;                                      // about 512 candidates per warp
+  while (w < tw && w * 512 < c) w *= 2;
+  while (w < tw && static_cast<size_t>(tw / w) * dpad * 4 > 64 * 1024) w *= 2;      // staged queries must fit shared memory
+#define VDB_GO(KP, W, TW) \
+  return launch_rerank<KP, W, TW>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s)
+#define VDB_PICK(KP, TW)                        \
+  switch (w) {                                  \
+    case 1: VDB_GO(KP, 1, TW);                  \
+    case 2: VDB_GO(KP, 2, TW);                  \
+    case 4: VDB_GO(KP, 4, TW);                  \
+    default: VDB_GO(KP, TW, TW);                \
   }
+  switch (kp) {
+    case 32: VDB_PICK(32, 8)
+    case 128: VDB_PICK(128, 8)
+    case 256: VDB_PICK(256, 8)
+    default: VDB_PICK(512, 4)
+  }
+#undef VDB_PICK
+#undef VDB_GO
 }

@@ -79,24 +79,34 @@ struct WarpTopK {
   }
 };
 
-// Merge the W warp pools of a CTA (warp 0 does it) and write the best k as (distance, id).
+// Barrier over the NT threads that serve one query (a CTA holds 256 / NT such groups; id 1..8, 0 is __syncthreads).
+template <int NT>
+__device__ __forceinline__ void group_sync(int id) {
+  if constexpr (NT == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NT) : "memory");
+}
+
+// Merge the W warp pools of one query (the group's warp 0 does it) and write the best k as (distance, id).
 //   key -> distance: L2: key (or sqrt), IP: key = -score.
+// W warps serve one query; a CTA may hold several such groups (small probe counts / candidate sets: one
+// query per 8 warps leaves every warp a handful of rows, no pool ever fills, and the group's single merging
+// warp walks W nearly empty pools).  pools_smem / cnts_smem / thr_s are the GROUP's arrays, `warp` the warp's
+// index inside the group, bar_id the group's barrier.
 template <int KP, int W>
-__device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* pools_smem, int* cnts_smem, int warp, int lane,
-                                               int metric, int k, int flags, float pad_value, int64_t id_offset,
-                                               float* out_d, int64_t* out_i) {
+__device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* pools_smem, int* cnts_smem, float* thr_s, int warp,
+                                               int lane, int bar_id, int metric, int k, int flags, float pad_value,
+                                               int64_t id_offset, float* out_d, int64_t* out_i) {
   constexpr int CAP = pool_cap(KP);
   constexpr int E = KP / 32;
-  // The tightest of the warps' bounds is a bound for the whole CTA (that warp alone holds KP keys
+  // The tightest of the warps' bounds is a bound for the whole query (that warp alone holds KP keys
   // below it), so every warp first drops what lies above it from its own pool - in parallel - and
   // the serial merge below sees little more than KP entries instead of up to W * CAP.
-  __shared__ float thr_s[W];
-  if (lane == 0) thr_s[warp] = mine.thr;
-  __syncthreads();
-  float gthr = thr_s[0];
+  if constexpr (W > 1) {
+    if (lane == 0) thr_s[warp] = mine.thr;
+    group_sync<W * 32>(bar_id);
+    float gthr = thr_s[0];
 #pragma unroll
-  for (int w = 1; w < W; ++w) gthr = fminf(gthr, thr_s[w]);
-  {
+    for (int w = 1; w < W; ++w) gthr = fminf(gthr, thr_s[w]);
     const uint32_t cut = f2ord(gthr);
     int kept = 0;
     for (int base = 0; base < mine.cnt; base += 32) {
@@ -112,7 +122,7 @@ __device__ __forceinline__ void cta_write_topk(WarpTopK<KP>& mine, uint64_t* poo
     mine.cnt = kept;
   }
   if (lane == 0) cnts_smem[warp] = mine.cnt;
-  __syncthreads();
+  group_sync<W * 32>(bar_id);
   if (warp != 0) return;
   // the W pools are walked as one virtual list, KP entries per merge step: short lists (small
   // nprobe, few candidates) then cost one or two merges instead of one per warp

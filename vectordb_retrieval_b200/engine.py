@@ -457,10 +457,11 @@ class IVFShard:
             _, probes = self.quantizer.search(q, nprobe)
             out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
             out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
-            check(self.lib.vdb_ivf_scan_topk(metric_code(self.metric), ptr(self.list_vecs), ptr(self.list_ids),
-                                             ptr(self.blk_off), self.nlist, self.d, ptr(probes), nprobe, ptr(q),
-                                             q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
-                                             ptr(scanned), _stream(self.dev)), "vdb_ivf_scan_topk")
+            rows_hint = max(1, nprobe * self.n // max(self.nlist, 1))     # expected rows per query -> warps per query
+            check(self.lib.vdb_ivf_scan_topk_ex(metric_code(self.metric), ptr(self.list_vecs), ptr(self.list_ids),
+                                                ptr(self.blk_off), self.nlist, self.d, ptr(probes), nprobe, ptr(q),
+                                                q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
+                                                ptr(scanned), rows_hint, _stream(self.dev)), "vdb_ivf_scan_topk")
         self.last_probes = probes
         return out_d, out_i
 
