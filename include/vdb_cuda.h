@@ -226,7 +226,7 @@ int vdb_ivf_scan_topk_ex(int metric, const float* list_vecs, const int32_t* list
  * scan.  Operands: vdb_hamming_tc_expand turns packed codes [n, words] into bf16 rows of
  * vdb_hamming_tc_row_bytes(nbits) bytes for rows_pad >= n rows (rows_pad = vdb_flat_npad(n) for the
  * base together with norms [rows_pad], vdb_flat_nqpad(nq) and negate = 1 for the queries).  The packed
- * codes are still needed for the sampled bound.  n > 65536. */
+ * codes are still needed for the sampled bound.  65536 < n <= 8388608 (2^23). */
 int vdb_hamming_tc_row_bytes(int nbits);
 int vdb_hamming_tc_expand(const uint32_t* codes, int64_t n, int words, int nbits, int negate, void* out, float* norms,
                           int64_t rows_pad, void* stream);

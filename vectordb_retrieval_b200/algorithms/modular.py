@@ -350,10 +350,21 @@ class FaissSearcher(BaseSearcher):
                 if self.normalize_queries:
                     engine.normalize_rows_(qc)
                 _, cand = self.index.search_device(qc, candidate_k)
+                empty_rows = np.empty(0, dtype=np.int64)           # our Hamming top-k always fills min(candidate_k, ntotal) slots
             else:
-                _, cand_host = self.index.search(self._host_queries(queries), candidate_k)
-                cand = torch.from_numpy(np.ascontiguousarray(cand_host, dtype=np.int64)).to(rr.dev)
-            return engine.results_to_host(*rr.search(q, cand, int(k), flags, float("inf")))
+                hq = self._host_queries(queries)
+                _, cand_host = self.index.search(hq, candidate_k)
+                cand_host = np.ascontiguousarray(cand_host, dtype=np.int64)
+                empty_rows = np.nonzero((cand_host >= 0).sum(axis=1) == 0)[0]
+                cand = torch.from_numpy(cand_host).to(rr.dev)
+            dist, idx = engine.results_to_host(*rr.search(q, cand, int(k), flags, float("inf")))
+            if empty_rows.size:
+                # a query without a single valid candidate takes the raw index order (modular.py:486-493)
+                raw_d, raw_i = self.index.search(hq[empty_rows], k)
+                raw_d = np.asarray(raw_d, dtype=np.float32)
+                dist[empty_rows] = -raw_d if self.metric in {"cosine", "ip"} else raw_d
+                idx[empty_rows] = np.asarray(raw_i, dtype=np.int64)
+            return dist, idx
 
     def batch_search(self, queries: np.ndarray, k: int = 10) -> Tuple[np.ndarray, np.ndarray]:
         if not self._prepared:

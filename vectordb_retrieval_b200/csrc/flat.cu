@@ -558,7 +558,7 @@ static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUten
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(tc::kThreads);
+  cfg.blockDim = dim3(tc::threads<HAM>());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -795,11 +795,11 @@ __global__ void ham_expand_kernel(const uint32_t* __restrict__ codes, int64_t n,
 }
 
 // Selection over what the scan collected for a query (lists per segment, rows ascending, every key
-// within the sampled bound): histogram of the distances in shared memory, cut bin and tie budget, then
+// within the sampled bound; entry = distance << 23 | row): histogram of the distances in shared memory, cut bin and tie budget, then
 // a stable placement pass - segments and rows arrive ascending, so equal distances keep id order.
 // A query whose lists overflowed or hold fewer than `need` entries is flagged for the exact popc path.
 __global__ void __launch_bounds__(128)
-ham_select_kernel(const uint64_t* __restrict__ list, const int* __restrict__ lcnt, int segs, int cap, int64_t nq, int nbits,
+ham_select_kernel(const uint32_t* __restrict__ list, const int* __restrict__ lcnt, int segs, int cap, int64_t nq, int nbits,
                   int k, int need, int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i,
                   uint8_t* __restrict__ fallback) {
   extern __shared__ int cur_all[];                     // [4][nbits + 2]
@@ -824,8 +824,8 @@ ham_select_kernel(const uint64_t* __restrict__ list, const int* __restrict__ lcn
   if (lane == 0) fallback[q] = 0;
   for (int s = 0; s < segs; ++s) {
     const int c = lcnt[static_cast<int64_t>(s) * nq + q];
-    const uint64_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
-    for (int i = lane; i < c; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 32), 1);
+    const uint32_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
+    for (int i = lane; i < c; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 23), 1);
   }
   __syncwarp();
   int t = bins, tie_budget = 0;
@@ -847,12 +847,12 @@ ham_select_kernel(const uint64_t* __restrict__ list, const int* __restrict__ lcn
   int seen = 0;                                        // ties of the cut bin met so far (warp-uniform)
   for (int s = 0; s < segs; ++s) {
     const int c = lcnt[static_cast<int64_t>(s) * nq + q];
-    const uint64_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
+    const uint32_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
     for (int base = 0; base < c; base += 32) {
       const int i = base + lane;
       const bool valid = i < c;
-      const uint64_t w = valid ? src[i] : 0ull;
-      const int dist = valid ? static_cast<int>(w >> 32) : -1;
+      const uint32_t w = valid ? src[i] : 0u;
+      const int dist = valid ? static_cast<int>(w >> 23) : -1;
       const bool tie = valid && dist == t;
       const unsigned tie_m = __ballot_sync(0xffffffffu, tie);
       const bool takes = valid && (dist < t || (tie && seen + __popc(tie_m & lt_mask) < tie_budget));
@@ -862,7 +862,7 @@ ham_select_kernel(const uint64_t* __restrict__ list, const int* __restrict__ lcn
         const int slot = cur[dist] + __popc(peers & lt_mask);
         if (slot < k) {
           out_d[q * k + slot] = static_cast<float>(dist);
-          out_i[q * k + slot] = static_cast<int64_t>(static_cast<uint32_t>(w)) + id_offset;
+          out_i[q * k + slot] = static_cast<int64_t>(w & 0x7fffffu) + id_offset;
         }
       }
       __syncwarp();
@@ -1058,9 +1058,9 @@ size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n) {
   int sm = 148;
   vdb_sm_count(&sm);
   const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, vdb_flat_npad(n), rb / 4, sm);
-  const int64_t segs = plan.n_chunks;
+  const int64_t segs = 2 * plan.n_chunks;                     // every chunk is drained as two segments (flat_tc.cuh)
   const int cap = ham_list_cap(n, k, static_cast<int>(segs));
-  return align256(static_cast<size_t>(segs) * nq * cap * 8) + align256(static_cast<size_t>(segs) * nq * 4) +
+  return align256(static_cast<size_t>(segs) * nq * cap * 4) + align256(static_cast<size_t>(segs) * nq * 4) +
          2 * align256(static_cast<size_t>(nq) * 4) + align256(static_cast<size_t>(nq) * (nbits + 1) * 4) +
          align256(vdb_hamming_topk_workspace_bytes(nq, nbits)) + 256;
 }
@@ -1069,7 +1069,8 @@ int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_
                         const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
                         int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
   const int rb = vdb_hamming_tc_row_bytes(nbits);
-  VDB_REQUIRE(rb != 0 && n > 65536 && nq > 0 && k >= 1 && n < (int64_t(1) << 32), "vdb_hamming_topk_tc: bad shape (nbits <= 256, n > 65536)");
+  VDB_REQUIRE(rb != 0 && n > 65536 && nq > 0 && k >= 1 && vdb_flat_npad(n) <= (int64_t(1) << 23),
+              "vdb_hamming_topk_tc: bad shape (nbits <= 256, 65536 < n <= 8388608: list entries hold a 23-bit row)");
   VDB_REQUIRE(workspace != nullptr && workspace_bytes >= vdb_hamming_tc_workspace_bytes(nq, nbits, k, n),
               "vdb_hamming_topk_tc: workspace too small");
   int sm = 0;
@@ -1078,11 +1079,11 @@ int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_
   const int kpad = rb / 4;                                     // the code rows seen as fp32 rows: same bytes, same tiles
   const int64_t n_pad = vdb_flat_npad(n), nq_pad = vdb_flat_nqpad(nq);
   const FlatPlan plan = make_plan(VDB_IMPL_TCGEN05, nq, n_pad, kpad, sm);
-  const int segs = plan.n_chunks, bins = nbits + 1;
+  const int segs = 2 * plan.n_chunks, bins = nbits + 1;
   const int cap = ham_list_cap(n, k, segs);
   uint8_t* w = static_cast<uint8_t*>(workspace);
   size_t off = 0;
-  uint64_t* list = reinterpret_cast<uint64_t*>(w + off); off += align256(static_cast<size_t>(segs) * nq * cap * 8);
+  uint32_t* list = reinterpret_cast<uint32_t*>(w + off); off += align256(static_cast<size_t>(segs) * nq * cap * 4);
   int* lcnt = reinterpret_cast<int*>(w + off);           off += align256(static_cast<size_t>(segs) * nq * 4);
   int* T = reinterpret_cast<int*>(w + off);              off += align256(static_cast<size_t>(nq) * 4);
   uint8_t* fallback = w + off;                           off += align256(static_cast<size_t>(nq) * 4);

@@ -60,11 +60,13 @@ struct FlatScanParams {
   const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
   float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
   // Hamming scan (kHam, flat.cu): operands are bf16 +-1 codes (queries negated, so key = -dot and
-  // ham = (nbits + key) / 2); every key within the query's bound is appended to the (segment, query) list
+  // ham = (nbits + key) / 2); every key within the query's bound is appended to the (segment, query) list.
+  // A chunk is cut into two segments: its first ceil(n/2) tiles are drained by epilogue group 0 (warps 4..7, TMEM
+  // buffer 0), the rest by group 1 (warps 8..11, buffer 1); the issuer alternates between the two tile streams.
   int ham_nbits;
   const int* ham_bound; // [nq] bound T (-1 = query off)
-  uint64_t* ham_list;   // [n_chunks][nq][ham_cap] (distance << 32 | row), rows ascending inside a segment
-  int* ham_cnt;         // [n_chunks][nq] entries offered to the list (> ham_cap: the list overflowed)
+  uint32_t* ham_list;   // [2 * n_chunks][nq][ham_cap] (distance << 23 | row), rows ascending inside a segment and across segments
+  int* ham_cnt;         // [2 * n_chunks][nq] entries offered to the list (> ham_cap: the list overflowed)
   int ham_cap;
   int dbg;              // bring-up knob (vdb_set_debug_mode): 0 normal, 2 no appends, 3 no tcgen05.ld, 5 keep the previous call's bounds, 8/9 = 0/5 + counters
 };
@@ -76,6 +78,8 @@ constexpr int kSeedKeep = 16;   // chunk minima a query keeps per item of the se
 
 namespace tc {
 constexpr int kThreads = 256;
+constexpr int kThreadsHam = 384;                     // the Hamming scan runs a second epilogue group (warps 8..11)
+template <int kHam> constexpr int threads() { return kHam != 0 ? kThreadsHam : kThreads; }
 constexpr int kStages = 3;
 constexpr int kBlockRows = 128;                      // rows per operand block (A or B half)
 constexpr int kBlockBytes = kBlockRows * 128;        // 16 KB: 128 rows x 32 fp32, SWIZZLE_128B
@@ -98,7 +102,7 @@ constexpr int smem_bytes() {
 // insertion network, so the pass runs at the contraction's speed) and writes them out at the end of
 // the item; the r-th smallest of them over the sample is the query's starting bound for the main pass.
 template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, bool kSeed = false, int kHam = 0>
-__global__ void __launch_bounds__(tc::kThreads, 1)
+__global__ void __launch_bounds__(tc::threads<kHam>(), 1)
 flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     const FlatScanParams P) {
@@ -168,6 +172,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
+      uint32_t ham_use[2] = {0u, 0u};             // kHam: uses of each norm / TMEM buffer so far
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int chunk = item / P.n_qtiles, qt = item % P.n_qtiles;
         if (P.qtile_active != nullptr && __ldg(P.qtile_active + qt) == 0) continue;   // every role skips the same items
@@ -184,7 +189,10 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           if (is_leader) mbar_arrive_expect_tx(a_full_bar, kCtaGroup * P.kb * kOps * tc::kBlockBytes);
           else mbar_arrive_cluster(a_full_bar, 0);
         }
-        for (int t = t0; t < t1; ++t, ++tile_iter) {
+        const int n_item = t1 - t0, n_first = (n_item + 1) >> 1;      // kHam: tiles of the item, of its first segment
+        for (int ts = 0; ts < n_item; ++ts, ++tile_iter) {
+          // kHam: alternate between the item's two segments (even step: group 0 / buffer 0, odd: group 1 / buffer 1)
+          const int t = kHam != 0 ? ((ts & 1) ? t0 + n_first + (ts >> 1) : t0 + (ts >> 1)) : t0 + ts;
           const int b_row0 = t * P.tile_stride * UMMA_N + cta_rank * 128;
           for (int kbi = 0; kbi < P.kb; ++kbi) {
             mbar_wait(empty_bar + stage, phase ^ 1);
@@ -201,8 +209,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           }
           // |x|^2 of the whole tile for this CTA's epilogue (issued after the operand loads, so the
           // wait for the previous user of this buffer never delays them)
-          const uint32_t nbuf = tile_iter & 1;
-          mbar_wait(norm_empty_bar + nbuf, ((tile_iter >> 1) & 1) ^ 1);
+          uint32_t nbuf = tile_iter & 1, nuse = tile_iter >> 1;       // buffer, and how often it was used before
+          if constexpr (kHam != 0) { nbuf = ts & 1; nuse = ham_use[nbuf]++; }
+          mbar_wait(norm_empty_bar + nbuf, (nuse & 1) ^ 1);
           mbar_arrive_expect_tx(norm_full_bar + nbuf, UMMA_N * 4);
           bulk_load_1d(norm_ring + nbuf * UMMA_N, P.norms + static_cast<int64_t>(t) * P.tile_stride * UMMA_N, UMMA_N * 4,
                        norm_full_bar + nbuf);
@@ -215,6 +224,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     // ===================================== MMA issuer (leader CTA) ==========================
     if (is_leader) {
       int stage = 0; uint32_t phase = 0; int item_iter = 0; uint32_t tile_iter = 0;
+      uint32_t ham_use[2] = {0u, 0u};
       for (int item = cluster_id; item < n_items; item += n_clusters) {
         const int chunk = item / P.n_qtiles;
         if (P.qtile_active != nullptr && __ldg(P.qtile_active + item % P.n_qtiles) == 0) continue;
@@ -222,8 +232,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         const int t1 = min(t0 + P.tiles_per_chunk, P.n_tiles);
         if (kAResident) { mbar_wait(a_full_bar, item_iter & 1); tc_fence_after(); }
         for (int t = t0; t < t1; ++t, ++tile_iter) {
-          const uint32_t buf = tile_iter & 1;
-          mbar_wait(tmem_empty_bar + buf, ((tile_iter >> 1) & 1) ^ 1);
+          uint32_t buf = tile_iter & 1, use = tile_iter >> 1;
+          if constexpr (kHam != 0) { buf = (t - t0) & 1; use = ham_use[buf]++; }    // only the step parity matters here
+          mbar_wait(tmem_empty_bar + buf, (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * UMMA_N;
           for (int kbi = 0; kbi < P.kb; ++kbi) {
@@ -301,12 +312,18 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       float thr = -CUDART_INF_F;
       float top[kSeedKeep];
       int ham_t = -1;
-      uint64_t* ham_out = nullptr;
+      uint32_t* ham_out = nullptr;
+      // kHam: this warp's epilogue group (0: warps 4..7, 1: warps 8..11) drains one of the item's two segments
+      const int n_item = t1 - t0, n_first = (n_item + 1) >> 1;
+      const int grp = kHam != 0 ? ((warp - 4) >> 2) : 0;
+      const int tb = kHam != 0 ? (grp != 0 ? t0 + n_first : t0) : t0;
+      const int te = kHam != 0 ? (grp != 0 ? t1 : t0 + n_first) : t1;
+      const int64_t ham_seg = static_cast<int64_t>(chunk) * 2 + grp;
       if constexpr (kHam != 0) {
         // keys are -dot (integers): ham <= b  <=>  key <= 2b - nbits; the filter compares with `<`
         if (live) ham_t = P.ham_bound[q];
         if (ham_t >= 0) thr = static_cast<float>(2 * ham_t - P.ham_nbits) + 0.5f;
-        ham_out = P.ham_list + (static_cast<int64_t>(chunk) * P.nq + (live ? q : 0)) * P.ham_cap;
+        ham_out = P.ham_list + (ham_seg * P.nq + (live ? q : 0)) * P.ham_cap;
       } else if constexpr (kSeed) {
 #pragma unroll
         for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
@@ -319,8 +336,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         if (gen > 0 || P.qtile_active != nullptr) cnt = __ldcg(P.pool_cnt + pool_id);
         if (live) thr = ld_volatile_thr(thr_g);
       }
-      for (int t = t0; t < t1; ++t, ++tile_iter) {
-        const uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
+      for (int t = tb; t < te; ++t, ++tile_iter) {
+        uint32_t buf = tile_iter & 1, ph = (tile_iter >> 1) & 1;
+        if constexpr (kHam != 0) { buf = grp; ph = tile_iter & 1; }   // the group owns its buffer: tile_iter counts its uses
         // the shared bound is read here and folded in after the tile: its latency hides behind the tile
         const uint32_t thr_seen = (kSeed || kHam != 0) ? 0u : ld_volatile_thr_raw(thr_g);   // branch-free; converted where it is used
         const uint32_t row0 = static_cast<uint32_t>(t * P.tile_stride) * UMMA_N;
@@ -399,9 +417,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     // branch-free like the flat scan's appends: the per-key test only predicates the store
                     const float key = __uint_as_float(v[g * 4 + u]);
                     const bool hit = key < thr;                        // ham <= bound (padding rows carry +inf)
-                    const int ham = (P.ham_nbits + __float2int_rz(fminf(key, 1024.f))) >> 1;
-                    if (hit && cnt < P.ham_cap)
-                      ham_out[cnt] = (static_cast<uint64_t>(static_cast<uint32_t>(ham)) << 32) | (rbase + g * 4 + u);
+                    // key + nbits = 2 * ham (an even integer): shifted by 22 it is ham << 23, the row takes bits 0..22
+                    const uint32_t entry = (static_cast<uint32_t>(__float2int_rn(key) + P.ham_nbits) << 22) | (rbase + g * 4 + u);
+                    if (hit && cnt < P.ham_cap) ham_out[cnt] = entry;
                     cnt += hit ? 1 : 0;
                   }
                 }
@@ -446,7 +464,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         if (!kSeed && kHam == 0 && live) thr = fminf(thr, ord2f(thr_seen));
       }
       if constexpr (kHam != 0) {
-        if (live) P.ham_cnt[static_cast<int64_t>(chunk) * P.nq + q] = cnt;
+        if (live) P.ham_cnt[ham_seg * P.nq + q] = cnt;
       }
       if constexpr (kSeed) {
         float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);
