@@ -122,6 +122,41 @@ def test_faiss_searcher_lsh_rerank_with_injected_candidates(A, metric):
     np.testing.assert_allclose(dist, g[f"{metric}_D"], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_lsh_rerank_row_without_candidates_takes_the_raw_index_order(A, metric):
+    """reference src/algorithms/modular.py:486-493: a query whose candidate row holds no valid id is answered by
+    a second ``index.search(query, k)`` (values negated for ip / cosine); every other row is re-scored as usual."""
+    rng = np.random.RandomState(4)
+    base = rng.randn(200, 12).astype(np.float32)
+    queries = rng.randn(6, 12).astype(np.float32)
+    cand = np.stack([rng.permutation(200)[:40] for _ in range(6)]).astype(np.int64)
+    cand[2] = -1
+    raw_d = np.linspace(1.0, 2.0, 5, dtype=np.float32)[None, :]
+    raw_i = np.arange(100, 105, dtype=np.int64)[None, :]
+    calls = []
+
+    class Fake:
+        ntotal = 200
+
+        def search(self, q, k):
+            calls.append((q.shape[0], k))
+            if k == 40:
+                return np.zeros((q.shape[0], k), dtype=np.float32), cand[: q.shape[0]]
+            np.testing.assert_allclose(q, queries[2:3], rtol=1e-6)
+            return np.repeat(raw_d, q.shape[0], 0), np.repeat(raw_i, q.shape[0], 0)
+
+    s = A.FaissSearcher("s", 12, metric, lsh_candidate_multiplier=8.0)     # candidate_k = 40
+    s.attach(A.IndexArtifact(kind="faiss", data=Fake(), metadata={"metric": metric, "faiss_index_kind": "lsh"}), base)
+    dist, idx = s.batch_search(queries, 5)
+    assert calls == [(6, 40), (1, 5)]
+    np.testing.assert_array_equal(idx[2], raw_i[0])
+    np.testing.assert_allclose(dist[2], raw_d[0] if metric == "l2" else -raw_d[0])
+    ref_d, ref_i = oracle.rerank_search(base, cand, queries, 5, metric)
+    keep = [0, 1, 3, 4, 5]
+    np.testing.assert_array_equal(idx[keep], ref_i[keep])
+    np.testing.assert_allclose(dist[keep], ref_d[keep], rtol=1e-5, atol=2e-6)
+
+
 def test_reversed_candidates_kat(A):
     """reference tests/test_composite_algorithm.py:169-226: candidates arrive worst-first."""
     rng = np.random.RandomState(3)
