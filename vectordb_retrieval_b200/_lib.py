@@ -43,6 +43,7 @@ SIGNATURES = {
     "vdb_set_debug_mode": (_i32, [_i32]),
     "vdb_debug_read_prof": (_i32, [C.POINTER(C.c_uint64)]),
     "vdb_flat_set_seeding": (_i32, [_i32, _i32]),
+    "vdb_flat_set_seeding_margin": (_i32, [_i32]),
     "vdb_debug_redo_queries": (_i32, [C.POINTER(C.c_uint64)]),
     "vdb_merge_topk": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_merge_topk_strided": (_i32, [_p, _p, _i64, _i64, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),

@@ -105,6 +105,7 @@ static thread_local int g_debug_mode = 0;
 // for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) ~ 1e-10.
 static thread_local int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
 static thread_local int g_pre_rank = 16;      // r (1..32)
+static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(4, 128 / r)
 __device__ unsigned long long g_redo_queries;
 
 struct PrePlan {
@@ -134,7 +135,7 @@ static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, in
   PrePlan pp{};
   if (main_plan.cta_group == 0 || g_pre_tiles <= 0) return pp;
   const int r = std::min(std::max(g_pre_rank, 1), kSeedKeep);
-  const int margin = std::max(4, 128 / r);
+  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(4, 128 / r);
   const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
   const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
   if (s_tiles < 4) return pp;                       // small shard (< 64k rows at k' = 128): the sample would not pay for itself
@@ -907,6 +908,12 @@ int vdb_flat_set_seeding(int sample_tiles, int rank) {
   VDB_REQUIRE(sample_tiles >= 0 && rank >= 1 && rank <= kSeedKeep, "vdb_flat_set_seeding: sample_tiles >= 0, 1 <= rank <= %d", kSeedKeep);
   g_pre_tiles = sample_tiles;
   g_pre_rank = rank;
+  return 0;
+}
+
+int vdb_flat_set_seeding_margin(int margin) {
+  VDB_REQUIRE(margin >= 0 && margin <= 64, "vdb_flat_set_seeding_margin: 0 (default) .. 64");
+  g_pre_margin = margin;
   return 0;
 }
 
