@@ -458,7 +458,7 @@ def run_ours(args) -> int:
                         "are given too; algorithmic_tflops is the fp32-equivalent 2*nq*N_rank*d / t"}
 
     def e2e_block(m, mode):
-        h2d = NQ * DIM * 4 if mode != "queries" else ((NQ + world - 1) // world) * DIM * 4
+        h2d = NQ * DIM * 4 if world == 1 else ((NQ + world - 1) // world) * DIM * 4     # every rank uploads its query slice
         d2h = NQ * TOPK * 12 if world == 1 else ((NQ + world - 1) // world) * TOPK * 12
         return {"value": NQ / (m["e2e_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": m["e2e_ms"],
                 "h2d_bytes_per_step": h2d * (world if world > 1 else 1), "d2h_bytes_per_step": d2h * (world if world > 1 else 1),

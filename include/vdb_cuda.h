@@ -134,7 +134,7 @@ int vdb_debug_read_prof(uint64_t* out8);
 int vdb_flat_set_seeding(int sample_tiles, int rank);
 /* The sample is capped so that the guess's expected rank in the shard, rank * N / S rows, stays >= margin * k'
  * (k' = kept candidates, 128 for k = 100): a smaller margin allows a larger sample and a tighter guess on small
- * shards at a higher (still verified and repaired) chance of a redo.  0 = default max(4, 128 / rank). */
+ * shards at a higher (still verified and repaired) chance of a redo.  0 = default max(4, 64 / rank). */
 int vdb_flat_set_seeding_margin(int margin);
 /* Number of queries re-scanned since the last call (reads and clears a device counter). */
 int vdb_debug_redo_queries(uint64_t* out);
@@ -238,6 +238,13 @@ size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n);
 int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
                         const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
                         int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream);
+/* The same scan with fp16 operands (vdb_hamming_tc_expand with bit 1 of `negate` set: 2 = fp16 rows, 3 = fp16 and
+ * negated) and fp16 ACCUMULATORS: sums of +-1 products are integers of magnitude <= nbits <= 256, exact in fp16, and
+ * the epilogue reads the accumulators packed two per register (tcgen05.ld .pack::16b) and filters two keys per
+ * instruction.  Same results bit for bit.  nbits even. */
+int vdb_hamming_topk_tc_f16(const void* base_f16, const float* norms, const uint32_t* codes, int64_t n, const void* q_f16,
+                            const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                            int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

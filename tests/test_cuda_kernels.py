@@ -115,6 +115,31 @@ def test_integer_valued_data_with_exact_ties(eng):
     assert (I.cpu().numpy()[:20, 0] == np.arange(20)).all() and (I.cpu().numpy()[:20, 1] == np.arange(4000, 4020)).all()
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_tie_groups_wider_than_the_spare_slots_keep_the_lowest_ids(eng, impl):
+    """400 copies of one vector scattered over 90 000 rows, the query equal to it: 400 rows tie at distance 0, far
+    more than the k' - k spare pool slots.  The (distance, id) contract demands the 100 LOWEST ids whatever order
+    the scan meets the copies in - one shard, three shards + merge, tensor-core and CUDA-core kernels alike."""
+    from vectordb_retrieval_b200 import _lib
+    rng = np.random.RandomState(12)
+    n, d, k = 90_000, 32, 100
+    base = rng.randn(n, d).astype(np.float32)
+    dup = np.sort(rng.choice(n, 400, replace=False))
+    base[dup] = base[dup[0]]
+    q = np.vstack([base[dup[0]][None, :], rng.randn(40, d).astype(np.float32)])
+    qd = torch.from_numpy(q).cuda()
+    code = _lib.IMPL_NAMES[impl]
+    D, I = eng.FlatShard(base, "l2", "cuda").search(qd, k, 0, oracle.FLT_MAX, code)
+    np.testing.assert_array_equal(I.cpu().numpy()[0], dup[:k])
+    assert float(D[0].abs().max()) == 0.0
+    ref = oracle.faiss_flat_search(base, q[1:], k, "l2")
+    _check(ref, (D.cpu().numpy()[1:], I.cpu().numpy()[1:]))
+    bounds = [0, 29_999, 61_000, n]
+    parts = [eng.FlatShard(base[a:b], "l2", "cuda", id_offset=a).search(qd, k, 0, oracle.FLT_MAX, code) for a, b in zip(bounds[:-1], bounds[1:])]
+    Dm, Im = eng.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(Im, I) and torch.equal(Dm, D)
+
+
 def test_id_offset_and_merge_is_shard_count_invariant(eng):
     base, q = _data(9000, 64, 300, seed=9)
     ref = oracle.faiss_flat_search(base, q, 50, "l2")
@@ -385,7 +410,8 @@ def test_seeded_bounds_one_cta_variant_and_streamed_query_tile(eng):
         _check(oracle.faiss_flat_search(base, q, k, "l2"), (D.cpu().numpy(), I.cpu().numpy()))
 
 
-@pytest.mark.parametrize("nbits,d,n,nq,k", [(256, 50, 70000, 300, 700), (128, 32, 66000, 260, 64), (200, 24, 90000, 257, 1500)])
+@pytest.mark.parametrize("nbits,d,n,nq,k", [(256, 50, 70000, 300, 700), (128, 32, 66000, 260, 64), (200, 24, 90000, 257, 1500),
+                                            (255, 40, 70001, 256, 300), (64, 16, 69999, 300, 40000)])
 def test_hamming_topk_tensor_pipe_matches_popc_path(eng, nbits, d, n, nq, k):
     """The bf16 +-1 contraction path must return exactly what the popc path returns: same distances,
     same ids, (distance, id) order - including queries whose sampled bound is too small (duplicated
@@ -401,8 +427,10 @@ def test_hamming_topk_tensor_pipe_matches_popc_path(eng, nbits, d, n, nq, k):
     shard.tensor_pipe = False
     d0, i0 = shard.search(qd.clone(), k)
     shard.tensor_pipe = True
-    d1, i1 = shard.search(qd.clone(), k)
-    torch.cuda.synchronize()
-    np.testing.assert_array_equal(d0.cpu().numpy(), d1.cpu().numpy())
-    np.testing.assert_array_equal(i0.cpu().numpy(), i1.cpu().numpy())
-    assert (i1.cpu().numpy()[3, : 2 * k + 1] >= 0).all()
+    for f16 in (True, False):        # fp16 operands + accumulators (packed epilogue) / bf16 operands + fp32 accumulators
+        shard.tc_accumulate_f16 = f16
+        d1, i1 = shard.search(qd.clone(), k)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(d0.cpu().numpy(), d1.cpu().numpy(), err_msg=f"f16={f16}")
+        np.testing.assert_array_equal(i0.cpu().numpy(), i1.cpu().numpy(), err_msg=f"f16={f16}")
+        assert (i1.cpu().numpy()[3, : 2 * k + 1] >= 0).all()

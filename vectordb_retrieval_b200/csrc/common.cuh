@@ -46,6 +46,11 @@ int hamming_topk_subset(const uint32_t* codes, int64_t n, const uint32_t* qcodes
 // low half = row index inside the shard.  Unsigned compare == (key, row) lexicographic compare,
 // which makes every selection deterministic and independent of how the base is sharded.
 constexpr uint64_t kEmpty = ~0ull;
+// "No bound yet": the largest finite float, NOT +inf.  Keys are admitted with `key <= bound` so that a row whose key
+// EQUALS the running k'-th key still competes on its row id (the compaction keeps the lowest rows of a tie group;
+// with `<` a late low-id duplicate was dropped and the result depended on the scan order, i.e. on the sharding).
+// Padding rows carry +inf norms, hence +inf keys, and must never pass: +inf <= FLT_MAX is false.
+constexpr float kOpenBound = 3.402823466e+38f;
 
 __host__ __device__ __forceinline__ uint32_t f2ord(float f) {
 #ifdef __CUDA_ARCH__

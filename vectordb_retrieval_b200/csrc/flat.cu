@@ -105,7 +105,7 @@ static thread_local int g_debug_mode = 0;
 // for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) ~ 1e-10.
 static thread_local int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
 static thread_local int g_pre_rank = 16;      // r (1..32)
-static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(4, 128 / r)
+static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(4, 64 / r)
 __device__ unsigned long long g_redo_queries;
 
 struct PrePlan {
@@ -125,7 +125,7 @@ static thread_local bool g_ev_made = false;
 __global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, int64_t n_cnt, int* handover,
                                  int64_t n_hand, int keep_thr, int* active, int64_t n_active) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < nq_pad && !keep_thr) thr[i] = f2ord(CUDART_INF_F);
+  if (i < nq_pad && !keep_thr) thr[i] = f2ord(kOpenBound);
   if (i < n_cnt) pool_cnt[i] = 0;
   if (i < n_hand) handover[i] = 0;
   if (i < n_active) active[i] = 0;
@@ -135,7 +135,7 @@ static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, in
   PrePlan pp{};
   if (main_plan.cta_group == 0 || g_pre_tiles <= 0) return pp;
   const int r = std::min(std::max(g_pre_rank, 1), kSeedKeep);
-  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(4, 128 / r);
+  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(4, 64 / r);    // r = 16: 4 (was 8: 18 % slower on a 125k-row shard)
   const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
   const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
   if (s_tiles < 4) return pp;                       // small shard (< 64k rows at k' = 128): the sample would not pay for itself
@@ -175,7 +175,7 @@ flat_tau_kernel(const float* __restrict__ seed, int n_chunks, int64_t nq, int ra
   }
   const uint64_t w = __shfl_sync(0xffffffffu, best[0], rank - 1);
   if (lane == 0) {
-    uint32_t t = w == kEmpty ? f2ord(CUDART_INF_F) : static_cast<uint32_t>(w >> 32);
+    uint32_t t = w == kEmpty ? f2ord(kOpenBound) : min(static_cast<uint32_t>(w >> 32), f2ord(kOpenBound));   // never +inf: padding rows must not pass
     if (force_fail) t = f2ord(-CUDART_INF_F);       // test hook: every query must take the redo pass
     thr[q] = t;
   }
@@ -198,7 +198,7 @@ __global__ void flat_verify_kernel(int* pool_cnt, int n_pools, int64_t nq, int64
   }
   if (failed) {
     for (int s = 0; s < n_pools; ++s) pool_cnt[i * n_pools + s] = 0;
-    thr[i] = f2ord(CUDART_INF_F);
+    thr[i] = f2ord(kOpenBound);
     qtile_active[i / tile_rows] = 1;
     atomicAdd(&g_redo_queries, 1ull);
   } else {
@@ -271,7 +271,7 @@ flat_scan_simt_kernel(const float* __restrict__ b_hi, const float* __restrict__ 
           const uint32_t row = static_cast<uint32_t>(b_row0) + c * 32 + i;
           const float key = Ss[tid][c * 32 + i] + __ldg(P.norms + row);   // queries carry the -2
           if (P.dense != nullptr && live) P.dense[q * P.dense_ld + row] = key;
-          if (key < thr) { pool[cnt] = pack_key(key, row); ++cnt; }
+          if (key <= thr) { pool[cnt] = pack_key(key, row); ++cnt; }
         }
       }
     }
@@ -770,14 +770,15 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
 //   ascending) -> stable counting sort per query = (distance, id) order.  Queries whose sampled bound
 //   turns out too small are recounted without a bound by a second launch over their query tiles only.
 __global__ void ham_expand_kernel(const uint32_t* __restrict__ codes, int64_t n, int words, int nbits, int kwords,
-                                  int negate, uint4* __restrict__ out, float* __restrict__ norms, int64_t rows_pad) {
+                                  int negate, int fp16, uint4* __restrict__ out, float* __restrict__ norms, int64_t rows_pad) {
   // thread = (row, 32-bit word): writes 32 bf16 values (64 bytes)
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows_pad * kwords) return;
   const int64_t row = i / kwords;
   const int w = static_cast<int>(i % kwords);
   const uint32_t bits = row < n && w < words ? codes[row * words + w] : 0u;
-  const uint32_t one = negate ? 0xBF80u : 0x3F80u, minus = negate ? 0x3F80u : 0xBF80u;   // bf16 +1.0 / -1.0
+  const uint32_t p1 = fp16 ? 0x3C00u : 0x3F80u, m1 = fp16 ? 0xBC00u : 0xBF80u;            // +1.0 / -1.0 as fp16 or bf16
+  const uint32_t one = negate ? m1 : p1, minus = negate ? p1 : m1;
   uint32_t pk[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -801,7 +802,7 @@ __global__ void ham_expand_kernel(const uint32_t* __restrict__ codes, int64_t n,
 // A query whose lists overflowed or hold fewer than `need` entries is flagged for the exact popc path.
 __global__ void __launch_bounds__(128)
 ham_select_kernel(const uint32_t* __restrict__ list, const int* __restrict__ lcnt, int segs, int cap, int64_t nq, int nbits,
-                  int k, int need, int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i,
+                  int k, int need, uint32_t n_rows, int64_t id_offset, float* __restrict__ out_d, int64_t* __restrict__ out_i,
                   uint8_t* __restrict__ fallback) {
   extern __shared__ int cur_all[];                     // [4][nbits + 2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -811,23 +812,28 @@ ham_select_kernel(const uint32_t* __restrict__ list, const int* __restrict__ lcn
   int* cur = cur_all + warp * (bins + 1);
   for (int b = lane; b <= bins; b += 32) cur[b] = 0;
   __syncwarp();
-  long long total = 0;
   bool over = false;
+  for (int s = 0; s < segs; ++s) over |= lcnt[static_cast<int64_t>(s) * nq + q] > cap;
+  if (over) {
+    if (lane == 0) fallback[q] = 1;
+    return;
+  }
+  // histogram of the collected distances; padding rows (row >= n_rows: the fp16 scan does not mask them) are skipped
+  int mine = 0;
   for (int s = 0; s < segs; ++s) {
     const int c = lcnt[static_cast<int64_t>(s) * nq + q];
-    over |= c > cap;
-    total += c;
+    const uint32_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
+    for (int i = lane; i < c; i += 32) {
+      const uint32_t w = src[i];
+      if ((w & 0x7fffffu) < n_rows) { atomicAdd(cur + static_cast<int>(w >> 23), 1); ++mine; }
+    }
   }
-  if (over || total < need) {
+  const int total = __reduce_add_sync(0xffffffffu, mine);
+  if (total < need) {                                 // the sampled bound was too tight: exact popc path for this query
     if (lane == 0) fallback[q] = 1;
     return;
   }
   if (lane == 0) fallback[q] = 0;
-  for (int s = 0; s < segs; ++s) {
-    const int c = lcnt[static_cast<int64_t>(s) * nq + q];
-    const uint32_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
-    for (int i = lane; i < c; i += 32) atomicAdd(cur + static_cast<int>(src[i] >> 23), 1);
-  }
   __syncwarp();
   int t = bins, tie_budget = 0;
   if (lane == 0) {                                     // bins -> output offsets; cut bin and its budget
@@ -851,8 +857,8 @@ ham_select_kernel(const uint32_t* __restrict__ list, const int* __restrict__ lcn
     const uint32_t* src = list + (static_cast<int64_t>(s) * nq + q) * cap;
     for (int base = 0; base < c; base += 32) {
       const int i = base + lane;
-      const bool valid = i < c;
-      const uint32_t w = valid ? src[i] : 0u;
+      const uint32_t w = i < c ? src[i] : 0xffffffffu;
+      const bool valid = i < c && (w & 0x7fffffu) < n_rows;
       const int dist = valid ? static_cast<int>(w >> 23) : -1;
       const bool tie = valid && dist == t;
       const unsigned tie_m = __ballot_sync(0xffffffffu, tie);
@@ -1045,7 +1051,7 @@ int vdb_hamming_tc_expand(const uint32_t* codes, int64_t n, int words, int nbits
   const int kwords = rb / 64;
   const int64_t threads = rows_pad * kwords;
   ham_expand_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      codes, n, words, nbits, kwords, negate, static_cast<uint4*>(out), norms, rows_pad);
+      codes, n, words, nbits, kwords, negate & 1, (negate >> 1) & 1, static_cast<uint4*>(out), norms, rows_pad);
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1072,9 +1078,9 @@ size_t vdb_hamming_tc_workspace_bytes(int64_t nq, int nbits, int k, int64_t n) {
          align256(vdb_hamming_topk_workspace_bytes(nq, nbits)) + 256;
 }
 
-int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
-                        const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
-                        int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
+static int hamming_topk_tc_impl(bool fp16, const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
+                                const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                                int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
   const int rb = vdb_hamming_tc_row_bytes(nbits);
   VDB_REQUIRE(rb != 0 && n > 65536 && nq > 0 && k >= 1 && vdb_flat_npad(n) <= (int64_t(1) << 23),
               "vdb_hamming_topk_tc: bad shape (nbits <= 256, 65536 < n <= 8388608: list entries hold a 23-bit row)");
@@ -1107,13 +1113,33 @@ int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_
   if (make_operand_map(&mq, static_cast<const float*>(q_bf16), nq_pad, kpad) ||
       make_operand_map(&mb, static_cast<const float*>(base_bf16), n_pad, kpad))
     return 3;
-  if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+  if (fp16) {
+    VDB_REQUIRE(nbits % 2 == 0, "vdb_hamming_topk_tc_f16: nbits must be even (the fp16 epilogue halves key + nbits exactly)");
+    if (launch_tc<2, true, 32, false, false, 2>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+  } else {
+    if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+  }
   ham_select_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, static_cast<size_t>(4) * (bins + 1) * sizeof(int), s>>>(
-      list, lcnt, segs, cap, nq, nbits, k, static_cast<int>(std::min<int64_t>(k, n)), id_offset, out_d, out_i, fallback);
+      list, lcnt, segs, cap, nq, nbits, k, static_cast<int>(std::min<int64_t>(k, n)), static_cast<uint32_t>(n), id_offset, out_d,
+      out_i, fallback);
   VDB_CHECK_CUDA(cudaGetLastError());
   count_launches(2);
   // queries whose bound was short or whose lists overflowed: the exact popc path, for them alone
   return hamming_topk_subset(codes, n, qcodes, nq, nbits, k, id_offset, out_d, out_i, popc_ws, fallback, s);
+}
+
+int vdb_hamming_topk_tc(const void* base_bf16, const float* norms, const uint32_t* codes, int64_t n, const void* q_bf16,
+                        const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                        int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
+  return hamming_topk_tc_impl(false, base_bf16, norms, codes, n, q_bf16, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace,
+                              workspace_bytes, stream);
+}
+
+int vdb_hamming_topk_tc_f16(const void* base_f16, const float* norms, const uint32_t* codes, int64_t n, const void* q_f16,
+                            const uint32_t* qcodes, int64_t nq, int nbits, int k, int64_t id_offset, float* out_d,
+                            int64_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
+  return hamming_topk_tc_impl(true, base_f16, norms, codes, n, q_f16, qcodes, nq, nbits, k, id_offset, out_d, out_i, workspace,
+                              workspace_bytes, stream);
 }
 
 }  // extern "C"

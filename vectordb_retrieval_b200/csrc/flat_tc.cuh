@@ -32,6 +32,7 @@
 //           (segment, query) list
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -113,7 +114,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   constexpr int TMEM_COLS = 2 * UMMA_N;       // double-buffered accumulator
   constexpr int CAP = pool_cap(KP);
   constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
-  constexpr uint32_t IDESC_BF16 = make_idesc_bf16(UMMA_M, UMMA_N);
+  constexpr uint32_t IDESC_BF16 = kHam == 2 ? make_idesc_f16_acc16(UMMA_M, UMMA_N) : make_idesc_bf16(UMMA_M, UMMA_N);
   static_assert(kHam == 0 || (kAResident && !kDense && !kSeed), "the Hamming scan uses the resident query tile");
   constexpr int kOps = kHam != 0 ? 1 : 2;      // operand arrays in use: hi only / hi and lo
 
@@ -364,6 +365,59 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           if (lane == 0) mbar_arrive(norm_empty_bar + buf);
           continue;
         }
+        if constexpr (kHam == 2) {
+          // ---- fp16 accumulators: 64 columns per load (.pack::16b), keys filtered two per instruction -------------
+          // keys are -dot, integers in [-nbits, nbits], exact in fp16.  Padding rows (zero codes, key 0) are NOT
+          // masked here: the selection kernel drops rows >= n.
+          const uint32_t thr2 = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(thr))) * 0x10001u;
+          // ham = (key + nbits) / 2; adding 1024 puts the integer into the low mantissa bits of the half
+          const uint32_t half2c = 0x38003800u;                                                  // (0.5, 0.5)
+          const uint32_t bias2 = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(0.5f * P.ham_nbits + 1024.f))) * 0x10001u;
+          auto consume16 = [&](uint32_t (&v)[32], int c) {
+            const uint32_t rbase = row0 + c * 64;
+            unsigned gmask = 0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t m = hmin2_u32(hmin2_u32(v[g * 4 + 0], v[g * 4 + 1]), hmin2_u32(v[g * 4 + 2], v[g * 4 + 3]));
+              gmask |= hany_lt2_u32(m, thr2) ? (1u << g) : 0u;
+            }
+            const unsigned um = __reduce_or_sync(0xffffffffu, gmask);
+            if (um == 0u) return;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (um & (1u << g)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t k2 = v[g * 4 + u];
+                  uint32_t hit_lo, hit_hi;
+                  hlt2_u32(k2, thr2, hit_lo, hit_hi);
+                  const uint32_t h2 = hfma2_u32(k2, half2c, bias2);            // low 10 bits of each half = ham
+                  const uint32_t row = rbase + g * 8 + u * 2;
+                  const uint32_t e_lo = (h2 << 23) | row, e_hi = ((h2 >> 16) << 23) | (row + 1u);
+                  if (hit_lo != 0u && cnt < P.ham_cap) ham_out[cnt] = e_lo;
+                  cnt += static_cast<int>(hit_lo);
+                  if (hit_hi != 0u && cnt < P.ham_cap) ham_out[cnt] = e_hi;
+                  cnt += static_cast<int>(hit_hi);
+                }
+              }
+            }
+          };
+          constexpr int NCH16 = UMMA_N / 64;
+          tmem_ld_32x32_pack16(taddr, va);
+#pragma unroll 1
+          for (int c = 0; c < NCH16; c += 2) {
+            tmem_ld_wait();
+            tmem_ld_32x32_pack16(taddr + (c + 1) * 64, vb);
+            consume16(va, c);
+            tmem_ld_wait();
+            if (c + 2 < NCH16) tmem_ld_32x32_pack16(taddr + (c + 2) * 64, va);
+            else release_tmem();
+            consume16(vb, c + 1);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(norm_empty_bar + buf);
+          continue;
+        }
         tmem_ld_32x32(taddr, va);
 
         auto consume = [&](uint32_t (&v)[32], int c) {
@@ -405,7 +459,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           // stores ~1550, smem transpose + ballot per hitting lane ~1100, redux + switch loop ~1090.
           unsigned gmask = 0;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) gmask |= gm[g] < thr ? (1u << g) : 0u;
+          for (int g = 0; g < 8; ++g) gmask |= (kHam != 0 ? gm[g] < thr : gm[g] <= thr) ? (1u << g) : 0u;   // flat: ties compete on the row id
           const unsigned um = __reduce_or_sync(0xffffffffu, gmask);
           if constexpr (kHam != 0) {
             if (um != 0u) {
@@ -438,7 +492,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 for (int u = 0; u < 4; ++u) {
                   const float key = __uint_as_float(v[g * 4 + u]);
                   const uint64_t packed = pack_key(key, rbase + g * 4 + u);
-                  const bool hit = key < thr;
+                  const bool hit = key <= thr;
                   if (hit) pool[cnt] = packed;
                   cnt += hit ? 1 : 0;
                 }

@@ -171,6 +171,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+// The same shape with .pack::16b: an fp16 accumulator occupies one 32-bit TMEM column per element (low half), the
+// load packs adjacent columns pairwise, so 32 registers carry 64 columns: r[j] = col 2j (low half) | col 2j+1 (high)
+__device__ __forceinline__ void tmem_ld_32x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Shared-memory matrix descriptor, K-major operand tile whose rows are exactly one 128-byte
 // swizzle atom wide (32 fp32): 8-row groups are 1024 bytes apart (SBO), LBO unused,
@@ -188,6 +201,35 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 // kind::f16 with bf16 operands (format 1), fp32 accumulate, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// kind::f16 with fp16 operands (format 0) AND fp16 accumulate (c_format 0), both operands K-major: sums of +-1
+// products are small integers, exact in fp16, and the epilogue can filter two keys per instruction
+__host__ __device__ constexpr uint32_t make_idesc_f16_acc16(int m, int n) {
+  return (0u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// packed-half helpers for the fp16 epilogue
+__device__ __forceinline__ uint32_t hmin2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// (a.lo < b.lo, a.hi < b.hi) as two 0/1 integers
+__device__ __forceinline__ void hlt2_u32(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f16x2 p|q, %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\tselp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// true when either half of a is below the matching half of b
+__device__ __forceinline__ bool hany_lt2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f16x2 p|q, %1, %2;\n\tor.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(a), "r"(b));
+  return r != 0u;
+}
+__device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
 }
 
 }}  // namespace vdb::ptx

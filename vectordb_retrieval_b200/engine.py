@@ -545,17 +545,18 @@ class HammingShard:
             out_d = torch.full((nq, k), float("inf"), dtype=torch.float32, device=self.dev)
             out_i = torch.full((nq, k), -1, dtype=torch.int64, device=self.dev)
             if self._use_tensor_pipe(nq, k):
-                base16, norms = self._expanded()
+                f16 = self.tc_accumulate_f16 and self.nbits % 2 == 0      # fp16 operands + fp16 accumulators (packed epilogue)
+                base16, norms = self._expanded(f16)
                 row_bytes = self.lib.vdb_hamming_tc_row_bytes(self.nbits)
                 nq_pad = self.lib.vdb_flat_nqpad(nq)
                 q16 = torch.empty(nq_pad * row_bytes, dtype=torch.uint8, device=self.dev)
-                check(self.lib.vdb_hamming_tc_expand(ptr(qc), nq, self.words, self.nbits, 1, ptr(q16), None, nq_pad,
-                                                     _stream(self.dev)), "vdb_hamming_tc_expand")
+                check(self.lib.vdb_hamming_tc_expand(ptr(qc), nq, self.words, self.nbits, 1 | (2 if f16 else 0), ptr(q16), None,
+                                                     nq_pad, _stream(self.dev)), "vdb_hamming_tc_expand")
                 nbytes = self.lib.vdb_hamming_tc_workspace_bytes(nq, self.nbits, k, self.n)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
-                check(self.lib.vdb_hamming_topk_tc(ptr(base16), ptr(norms), ptr(self.codes), self.n, ptr(q16), ptr(qc), nq,
-                                                   self.nbits, k, self.id_offset, ptr(out_d), ptr(out_i), ptr(ws), nbytes,
-                                                   _stream(self.dev)), "vdb_hamming_topk_tc")
+                scan = self.lib.vdb_hamming_topk_tc_f16 if f16 else self.lib.vdb_hamming_topk_tc
+                check(scan(ptr(base16), ptr(norms), ptr(self.codes), self.n, ptr(q16), ptr(qc), nq, self.nbits, k, self.id_offset,
+                           ptr(out_d), ptr(out_i), ptr(ws), nbytes, _stream(self.dev)), "vdb_hamming_topk_tc")
                 return out_d, out_i
             nbytes = self.lib.vdb_hamming_topk_workspace_bytes(nq, nbits_kernel)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
@@ -565,24 +566,27 @@ class HammingShard:
 
     # ---- tensor-pipe path: bf16 +-1 copies of the codes (512 bytes per row at 256 bits), built on first use
     tensor_pipe = "auto"      # "auto" | True | False
+    tc_accumulate_f16 = True  # tensor-pipe scan: fp16 operands and accumulators (even nbits); False = bf16 operands, fp32 accumulators
 
     def _use_tensor_pipe(self, nq: int, k: int) -> bool:
         if self.tensor_pipe is False or self.lib.vdb_hamming_tc_row_bytes(self.nbits) == 0:
             return False
         if self.words != self.lib.vdb_lsh_code_words(self.nbits) or self.n <= 65536 or k > self.n:
             return False
+        if self.lib.vdb_flat_npad(self.n) > (1 << 23):
+            return False                                   # list entries hold a 23-bit row
         if self.lib.vdb_hamming_tc_workspace_bytes(nq, self.nbits, k, self.n) > (8 << 30):
             return False                                   # candidate lists of huge batches: stay on the popc kernels
         return True if self.tensor_pipe is True else (nq >= 256 and self.n <= 8_000_000)
 
-    def _expanded(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _expanded(self, f16: bool) -> Tuple[torch.Tensor, torch.Tensor]:
         cached = getattr(self, "_bf16", None)
-        if cached is None:
+        if cached is None or cached[2] != f16:
             row_bytes = self.lib.vdb_hamming_tc_row_bytes(self.nbits)
             n_pad = self.lib.vdb_flat_npad(self.n)
             base16 = torch.empty(n_pad * row_bytes, dtype=torch.uint8, device=self.dev)
             norms = torch.empty(n_pad, dtype=torch.float32, device=self.dev)
-            check(self.lib.vdb_hamming_tc_expand(ptr(self.codes), self.n, self.words, self.nbits, 0, ptr(base16), ptr(norms),
-                                                 n_pad, _stream(self.dev)), "vdb_hamming_tc_expand")
-            cached = self._bf16 = (base16, norms)
-        return cached
+            check(self.lib.vdb_hamming_tc_expand(ptr(self.codes), self.n, self.words, self.nbits, 2 if f16 else 0, ptr(base16),
+                                                 ptr(norms), n_pad, _stream(self.dev)), "vdb_hamming_tc_expand")
+            cached = self._bf16 = (base16, norms, f16)
+        return cached[0], cached[1]

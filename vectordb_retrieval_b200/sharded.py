@@ -305,6 +305,7 @@ class DistributedFlatIndex:
         self.metric = metric
         self.exchange = exchange
         self._plans: dict = {}
+        self._qstage: dict = {}
 
     @classmethod
     def from_global(cls, vectors, metric: str = "l2", device=None, group=None, exchange: str = "alltoall") -> "DistributedFlatIndex":
@@ -343,14 +344,41 @@ class DistributedFlatIndex:
 
     def search_host(self, queries, k: int, flags: int = 0, pad_value: Optional[float] = None, impl: int = 0):
         """Host queries in, HOST result out (NumPy views of the ranks' shared pinned block, valid for the next
-        three calls): every rank uploads the batch, scans its rows, receives the lists of its query slice,
-        merges them and copies that slice device -> host."""
+        three calls).  Every rank uploads only ITS slice of the batch and an NVLink allgather replicates the
+        queries (nq*d*4 / world bytes over each PCIe link instead of the whole batch over all of them); then
+        every rank scans its rows, receives the lists of its query slice, merges them and copies that slice of
+        the result device -> host."""
+        import numpy as np
+        import torch.distributed as dist
         eng = self.engine
-        q = eng.queries_to_device(queries, self.shard.dev, self.shard.d)
-        if self.world == 1:
-            _, pad = _conventions(eng, self.metric, flags, pad_value)
-            return eng.results_to_host(*self.shard.search(q, k, flags, pad, impl))
-        return self._plan(flags, pad_value, impl).search_to_host(q, k)
+        if self.world == 1 or isinstance(queries, torch.Tensor):
+            q = eng.queries_to_device(queries, self.shard.dev, self.shard.d)
+            if self.world == 1:
+                _, pad = _conventions(eng, self.metric, flags, pad_value)
+                return eng.results_to_host(*self.shard.search(q, k, flags, pad, impl))
+            return self._plan(flags, pad_value, impl).search_to_host(q, k)
+        qh = np.asarray(queries)
+        if qh.ndim == 1:
+            qh = qh.reshape(1, -1)
+        if qh.ndim != 2 or qh.shape[1] != self.shard.d:
+            raise RuntimeError(f"query batch has shape {qh.shape}, expected [nq, {self.shard.d}]")
+        nq, d = qh.shape
+        per = _cdiv(nq, self.world)
+        buf = self._qstage.get(nq)
+        if buf is None:
+            self._qstage.clear()
+            buf = self._qstage[nq] = (torch.empty((per * self.world, d), dtype=torch.float32, device=self.shard.dev),
+                                      torch.zeros((per, d), dtype=torch.float32, device=self.shard.dev))
+        q_full, q_slice = buf
+        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        if hi > lo:
+            part = qh[lo:hi]
+            if part.dtype != np.float32 or not part.flags["C_CONTIGUOUS"]:
+                part = np.ascontiguousarray(part, dtype=np.float32)
+            q_slice[: hi - lo].copy_(torch.from_numpy(part) if part.flags["WRITEABLE"] else torch.from_numpy(part.copy()),
+                                     non_blocking=True)
+        dist.all_gather_into_tensor(q_full, q_slice, group=self.group)
+        return self._plan(flags, pad_value, impl).search_to_host(q_full[:nq], k)
 
 
 class ReplicatedFlatIndex:
