@@ -545,7 +545,10 @@ class HammingShard:
             out_d = torch.full((nq, k), float("inf"), dtype=torch.float32, device=self.dev)
             out_i = torch.full((nq, k), -1, dtype=torch.int64, device=self.dev)
             if self._use_tensor_pipe(nq, k):
-                f16 = self.tc_accumulate_f16 and self.nbits % 2 == 0      # fp16 operands + fp16 accumulators (packed epilogue)
+                # fp16 operands + accumulators (packed epilogue, half the filter instructions, a bigger append path):
+                # measured on 1.2M x 256 bits, 10k queries - faster from k ~ 2 000 up (k = 6 400: 10.7 vs 12.5 ms),
+                # slower below (k = 800: 8.7 vs 7.8 ms); "auto" switches there
+                f16 = self.nbits % 2 == 0 and (k >= 2048 if self.tc_accumulate_f16 == "auto" else bool(self.tc_accumulate_f16))
                 base16, norms = self._expanded(f16)
                 row_bytes = self.lib.vdb_hamming_tc_row_bytes(self.nbits)
                 nq_pad = self.lib.vdb_flat_nqpad(nq)
@@ -566,7 +569,8 @@ class HammingShard:
 
     # ---- tensor-pipe path: bf16 +-1 copies of the codes (512 bytes per row at 256 bits), built on first use
     tensor_pipe = "auto"      # "auto" | True | False
-    tc_accumulate_f16 = True  # tensor-pipe scan: fp16 operands and accumulators (even nbits); False = bf16 operands, fp32 accumulators
+    tc_accumulate_f16 = "auto"  # tensor-pipe scan: True = fp16 operands and accumulators (even nbits), False = bf16 operands and
+    #                             fp32 accumulators, "auto" = by k
 
     def _use_tensor_pipe(self, nq: int, k: int) -> bool:
         if self.tensor_pipe is False or self.lib.vdb_hamming_tc_row_bytes(self.nbits) == 0:
