@@ -293,8 +293,11 @@ def _measure(label, index, algo, q_dev, q_host_np, args, lib, dev, world, rank, 
     d_dev, i_dev = d_dev.clone(), i_dev.clone()          # the exchange buffers are reused by the end-to-end leg
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         d_host, i_host = algo.batch_search(q_host_np, TOPK)
+        e2e_steps.append(time.perf_counter() - ts)        # the call returns host arrays: every step is complete when it returns
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -303,6 +306,7 @@ def _measure(label, index, algo, q_dev, q_host_np, args, lib, dev, world, rank, 
     return {"label": label, "ms_per_step": float(total_ms.item()) / args.steps, "scan_ms": float(scan_mean.item()),
             "wall_ms_per_step": t_wall * 1e3 / args.steps, "launches": int(launches), "flush": flush,
             "e2e_ms": float(e2e_s.item()) * 1e3 / args.steps, "clocks": clocks, "shard_bytes": shard_bytes,
+            "e2e_step_ms": [min(e2e_steps) * 1e3, statistics.median(e2e_steps) * 1e3, max(e2e_steps) * 1e3],
             "device_result": (d_dev, i_dev), "host_result": (d_host, i_host)}
 
 
@@ -461,6 +465,7 @@ def run_ours(args) -> int:
         h2d = NQ * DIM * 4 if world == 1 else ((NQ + world - 1) // world) * DIM * 4     # every rank uploads its query slice
         d2h = NQ * TOPK * 12 if world == 1 else ((NQ + world - 1) // world) * TOPK * 12
         return {"value": NQ / (m["e2e_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": m["e2e_ms"],
+                "step_ms_min_median_max_rank0": m["e2e_step_ms"],
                 "h2d_bytes_per_step": h2d * (world if world > 1 else 1), "d2h_bytes_per_step": d2h * (world if world > 1 else 1),
                 "h2d_bytes_per_rank": h2d, "d2h_bytes_per_rank": d2h,
                 "api": "ExactSearch.batch_search(numpy pinned queries) -> (numpy distances, numpy ids)" +
