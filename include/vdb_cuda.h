@@ -169,10 +169,6 @@ int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld,
                     const int64_t* cand, int64_t nq, int c, const float* q, int64_t ld_q,
                     int k, int flags, float pad_value, float* out_d, int64_t* out_i, void* stream);
 
-/* Measurement / test hook (per host thread): 0 = always stage candidate rows in registers; 1 (default) = rows of
- * d <= 64 are staged in shared memory with 16-byte asynchronous copies.  Results are identical. */
-int vdb_rerank_set_async(int on);
-
 /* ---- LSH sign codes + Hamming top-k (candidate generator in front of the rerank) ------- */
 /* Code layout: [n, words] uint32, words = vdb_lsh_code_words(nbits) = 4 * ceil(nbits / 128)
  * (16-byte aligned rows, unused high bits zero); bit b of a row = [ x . P[b] >= 0 ].

@@ -48,7 +48,6 @@ SIGNATURES = {
     "vdb_merge_topk": (_i32, [_p, _p, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_merge_topk_strided": (_i32, [_p, _p, _i64, _i64, _i32, _i64, _i32, _i32, _f32, _p, _p, _p]),
     "vdb_rerank_topk": (_i32, [_i32, _p, _i64, _i32, _i64, _p, _i64, _i32, _p, _i64, _i32, _i32, _f32, _p, _p, _p]),
-    "vdb_rerank_set_async": (_i32, [_i32]),
     "vdb_lsh_code_words": (_i32, [_i32]),
     "vdb_lsh_encode": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p]),
     "vdb_hamming_topk_workspace_bytes": (_sz, [_i64, _i32]),

@@ -93,140 +93,6 @@ rerank_topk_kernel(int metric, const float* __restrict__ base, int64_t n, int dp
   cta_write_topk<KP, W>(sel, pools, cnts, thr_s, warp, lane, bar_id, metric, k, flags, pad_value, 0, out_d + q * k, out_i + q * k);
 }
 
-// ---- asynchronous-copy variant (d <= 96) ---------------------------------------------------------------------------
-// The register-staged kernel above keeps 16 rows x 128 bytes in flight per warp and cannot go further: every byte in
-// flight is a register, and at 64 registers the kernel already sits at 32 warps per SM (ncu: long_scoreboard 44-60 % of
-// the samples, 0.3-0.6 of the HBM rate).  Here a warp copies R candidate rows at a time with 16-byte cp.async into its
-// own shared-memory buffer (two buffers: batch b+1 is in flight while batch b is scored), so the bytes in flight cost
-// shared memory instead of registers: 2 x R x 4*dpad bytes per warp (R = 16 rows: 6.5 KB at d = 50).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int KP, int W, int TW, int R>
-__global__ void __launch_bounds__(TW * 32)
-rerank_topk_async_kernel(int metric, const float* __restrict__ base, int64_t n, int dpad, int64_t ld,
-                         const int64_t* __restrict__ cand, int64_t nq, int c, const float* __restrict__ qmat, int64_t ld_q,
-                         int k, int flags, float pad_value, float* __restrict__ out_d, int64_t* __restrict__ out_i) {
-  constexpr int CAP = pool_cap(KP);
-  constexpr int QPC = TW / W;
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint64_t* pools_all = reinterpret_cast<uint64_t*>(smem_dyn);
-  int* cnts_all = reinterpret_cast<int*>(pools_all + TW * CAP);
-  float* thr_all = reinterpret_cast<float*>(cnts_all + TW);
-  float* qs_all = thr_all + TW;                              // [QPC][dpad]
-  float* stage_all = qs_all + QPC * dpad;                    // [TW][2][R][dpad], 16-byte aligned (dpad % 4 == 0)
-  const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int group = warp_cta / W, warp = warp_cta % W;
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * QPC + group;
-  if (q >= nq) return;                                       // whole groups leave together
-  uint64_t* pools = pools_all + group * W * CAP;
-  int* cnts = cnts_all + group * W;
-  float* thr_s = thr_all + group * W;
-  float* qs = qs_all + group * dpad;
-  float* stage = stage_all + static_cast<size_t>(warp_cta) * 2 * R * dpad;
-  const int bar_id = 1 + group;
-  for (int j = warp * 32 + lane; j < dpad; j += W * 32) qs[j] = qmat[q * ld_q + j];
-  group_sync<W * 32>(bar_id);
-  WarpTopK<KP> sel;
-  sel.init(pools + warp * CAP);
-  const int sub = lane >> 3, sl = lane & 7;
-  const int64_t* cq = cand + q * c;
-  // this warp's candidates: batches of R, batch b covers [(b * W + warp) * R, +R)
-  const int n_batches = (c + W * R - 1) / (W * R);
-  auto batch_begin = [&](int b) { return (b * W + warp) * R; };
-  // issue the copies of one batch: lane = candidate for the id load; 8 lanes copy one 128-byte step of a row
-  auto issue = [&](int b, int buf, int64_t& my_id) {
-    const int c0 = batch_begin(b);
-    const int ci = c0 + lane;
-    my_id = (lane < R && ci < c) ? cq[ci] : -1;
-    if (my_id >= n) my_id = -1;
-    float* dst = stage + static_cast<size_t>(buf) * R * dpad;
-#pragma unroll 4
-    for (int r0 = 0; r0 < R; r0 += 4) {
-      const int r = r0 + sub;
-      const int64_t id = __shfl_sync(0xffffffffu, my_id, r);
-      if (id >= 0) {
-        const float* src = base + id * ld;
-        for (int j = sl * 4; j < dpad; j += 32) cp_async16(dst + r * dpad + j, src + j);
-      }
-    }
-    cp_async_commit();
-  };
-  int64_t id_cur = -1, id_nxt = -1;
-  if (n_batches > 0 && batch_begin(0) < c) issue(0, 0, id_cur);
-  else cp_async_commit();                                    // keeps the group count in step with the loop below
-  for (int b = 0; b < n_batches; ++b) {
-    const int buf = b & 1;
-    if (b + 1 < n_batches && batch_begin(b + 1) < c) issue(b + 1, buf ^ 1, id_nxt);
-    else { cp_async_commit(); id_nxt = -1; }
-    cp_async_wait<1>();                                      // batch b has landed (this lane's copies) ...
-    __syncwarp();                                            // ... and every other lane's
-    if (batch_begin(b) < c) {
-      const float* rows = stage + static_cast<size_t>(buf) * R * dpad;
-#pragma unroll 2
-      for (int r0 = 0; r0 < R; r0 += 16) {                   // 16 rows per push: 4 rows per 8-lane group
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        int64_t idv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) idv[u] = __shfl_sync(0xffffffffu, id_cur, r0 + u * 4 + sub);
-        for (int j = sl * 4; j < dpad; j += 32) {
-          const float4 y = *reinterpret_cast<const float4*>(qs + j);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * 4 + sub;
-            const float4 x = idv[u] >= 0 ? *reinterpret_cast<const float4*>(rows + r * dpad + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (metric == VDB_METRIC_L2) {
-              const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-              acc[u] += static_cast<double>(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
-            } else {
-              acc[u] += static_cast<double>(fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))));
-            }
-          }
-        }
-        float my_key = 0.f;
-        uint32_t my_row = 0u;
-        bool my_valid = false;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          double a = acc[u];
-          a += __shfl_xor_sync(0xffffffffu, a, 4);
-          a += __shfl_xor_sync(0xffffffffu, a, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 1);
-          if (sl == u) {
-            my_key = metric == VDB_METRIC_L2 ? static_cast<float>(a) : -static_cast<float>(a);
-            my_row = static_cast<uint32_t>(idv[u]);
-            my_valid = idv[u] >= 0;
-          }
-        }
-        sel.push(my_valid && sl < 4, my_key, my_row, lane);
-      }
-    }
-    __syncwarp();                                            // the buffer is free before the next batch is issued into it
-    id_cur = id_nxt;
-  }
-  cta_write_topk<KP, W>(sel, pools, cnts, thr_s, warp, lane, bar_id, metric, k, flags, pad_value, 0, out_d + q * k, out_i + q * k);
-}
-
-template <int KP, int W, int TW, int R>
-static int launch_rerank_async(int metric, const float* base, int64_t n, int dpad, int64_t ld, const int64_t* cand, int64_t nq,
-                               int c, const float* q, int64_t ld_q, int k, int flags, float pad_value, float* out_d,
-                               int64_t* out_i, cudaStream_t stream) {
-  constexpr int QPC = TW / W;
-  const size_t smem = static_cast<size_t>(TW) * pool_cap(KP) * 8 + TW * 8 + static_cast<size_t>(QPC) * dpad * 4 +
-                      static_cast<size_t>(TW) * 2 * R * dpad * 4;
-  auto kern = rerank_topk_async_kernel<KP, W, TW, R>;
-  if (smem > 48 * 1024) VDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<static_cast<unsigned>((nq + QPC - 1) / QPC), TW * 32, smem, stream>>>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k,
-                                                                             flags, pad_value, out_d, out_i);
-  count_launches(1);
-  VDB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 template <int KP, int W, int TW>
 static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int64_t ld, const int64_t* cand, int64_t nq,
                          int c, const float* q, int64_t ld_q, int k, int flags, float pad_value, float* out_d,
@@ -245,12 +111,6 @@ static int launch_rerank(int metric, const float* base, int64_t n, int dpad, int
 }  // namespace vdb
 
 using namespace vdb;
-
-static thread_local bool g_rerank_async = true;
-extern "C" int vdb_rerank_set_async(int on) {          // measurement / test hook: 0 = always the register-staged kernel
-  g_rerank_async = on != 0;
-  return 0;
-}
 
 extern "C" int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, int64_t ld, const int64_t* cand,
                                int64_t nq, int c, const float* q, int64_t ld_q, int k, int flags, float pad_value,
@@ -271,17 +131,8 @@ extern "C" int vdb_rerank_topk(int metric, const float* base, int64_t n, int d, 
   int w = 1;                                      // about 512 candidates per warp
   while (w < tw && w * 512 < c) w *= 2;
   while (w < tw && static_cast<size_t>(tw / w) * dpad * 4 > 64 * 1024) w *= 2;      // staged queries must fit shared memory
-  // d <= 64 and k <= 256: the asynchronous-copy kernel (16 rows per batch and warp staged in shared memory: 53 KB of
-  // staging per CTA at d = 50, three CTAs per SM); otherwise rows staged in registers
-  const bool use_async = dpad <= 64 && kp <= 256 && g_rerank_async;
-#define VDB_GO(KP, W, TW)                                                                                                      \
-  do {                                                                                                                         \
-    if constexpr (KP <= 256) {                                                                                                 \
-      if (use_async)                                                                                                           \
-        return launch_rerank_async<KP, W, TW, 16>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s); \
-    }                                                                                                                          \
-    return launch_rerank<KP, W, TW>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s);    \
-  } while (0)
+#define VDB_GO(KP, W, TW) \
+  return launch_rerank<KP, W, TW>(metric, base, n, dpad, ld, cand, nq, c, q, ld_q, k, flags, pad_value, out_d, out_i, s)
 #define VDB_PICK(KP, TW)                        \
   switch (w) {                                  \
     case 1: VDB_GO(KP, 1, TW);                  \
