@@ -214,7 +214,7 @@ int vdb_ivf_scan_topk(int metric, const float* list_vecs, const int32_t* list_id
                       float* out_d, int64_t* out_i, int64_t* scanned_rows, void* stream);
 
 /* Same scan with a hint for the launch shape: rows_per_query_hint ~ nprobe * (rows / nlist), the rows a query is
- * expected to scan.  The kernel gives a query one warp per ~512 expected rows (1, 2, 4 or 8 warps; a 256-thread CTA
+ * expected to scan.  The kernel gives a query one warp per ~4 096 expected rows (1, 2, 4 or 8 warps; a 256-thread CTA
  * then serves 8, 4, 2 or 1 queries), so short scans (nprobe 1..8 over ~300-row lists) are not dominated by per-query
  * fixed work.  0 = one query per CTA (what vdb_ivf_scan_topk does).  Results never depend on the hint. */
 int vdb_ivf_scan_topk_ex(int metric, const float* list_vecs, const int32_t* list_ids,

@@ -6,6 +6,8 @@
 // List layout "interleaved-32": block = 32 vectors stored as float4 [d4][32]; a warp reads one
 // 512-byte line per 4 dimensions with 128-bit loads, one vector per lane, no cross-lane
 // reduction.  HBM-bound: algorithmic bytes = scanned rows * d * 4.
+#include <cstdlib>
+
 #include "select.cuh"
 
 namespace vdb {
@@ -142,10 +144,12 @@ static int launch_scan(int metric, const float* vecs, const int32_t* ids, const 
   return 0;
 }
 
-// warps per query for an expected number of scanned rows per query: about 512 rows per warp, a power of two <= tw
+// warps per query for an expected number of scanned rows per query: about 4 096 rows per warp, a power of two <= tw.
+// Measured on 1.2M x 50, nlist 4096, 10k queries (scripts/perf_ivf.py): one warp per query is fastest up to nprobe 8
+// (2 400 rows: 0.77 ms against 1.09 ms with eight), two at nprobe 16-32, four at nprobe 64.
 static int warps_for_rows(int64_t rows, int tw) {
   int w = 1;
-  while (w < tw && static_cast<int64_t>(w) * 512 < rows) w *= 2;
+  while (w < tw && static_cast<int64_t>(w) * 4096 < rows) w *= 2;
   return w;
 }
 
@@ -197,6 +201,7 @@ int vdb_ivf_scan_topk_ex(int metric, const float* list_vecs, const int32_t* list
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int tw = kp == 512 ? 4 : 8;
   int w = rows_per_query_hint > 0 ? warps_for_rows(rows_per_query_hint, tw) : tw;
+  if (const char* e = getenv("VDB_IVF_WPQ")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) w = v < tw ? v : tw; }   // tuning override
   while (w < tw && static_cast<size_t>(tw / w) * (((d + 3) / 4 + 7) & ~7) * 16 > 64 * 1024) w *= 2;   // staged queries must fit shared memory
 #define VDB_GO(KP, W, TW)                                                                                              \
   return launch_scan<KP, W, TW>(metric, list_vecs, list_ids, blk_off, nlist, d, probes, nprobe, q, ld_q, nq, k, flags, \
