@@ -67,6 +67,15 @@ struct WarpTopK {
     cnt = st.cnt;
   }
 
+  // the same for words that are already packed (ordered key << 32 | row)
+  __device__ __forceinline__ void push_packed(bool valid, uint64_t w, int lane) {
+    if (cnt > CAP - 32) compact(lane);
+    const bool pass = valid && static_cast<uint32_t>(w >> 32) <= f2ord(thr);
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (pass) pool[cnt + __popc(m & ((1u << lane) - 1u))] = w;
+    cnt += __popc(m);
+  }
+
   // every lane of the warp calls; `valid` lanes offer one (key,row) each
   __device__ __forceinline__ void push(bool valid, float key, uint32_t row, int lane) {
     if (cnt > CAP - 32) compact(lane);
