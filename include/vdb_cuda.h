@@ -184,6 +184,22 @@ int vdb_hamming_topk(const uint32_t* codes, int64_t n, const uint32_t* qcodes, i
                      int k, int64_t id_offset, float* out_d, int64_t* out_i,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Python-LSH candidate generation (bucket union + vote order) ----------------------------------------- */
+/* Replaces LSHSearcher._gather_candidates / _select_candidates (src/algorithms/lsh.py:219-240): the union of a
+ * query's n_tables hash buckets in Counter.most_common() order (votes descending, first seen first), cut at `cap`.
+ *   tbl_ids   [n_tables * n_rows] int32: table t's rows grouped by bucket, insertion (= ascending row) order inside
+ *   seg_off   [nq, n_tables] int64: start of the query's bucket in tbl_ids (table offset included); seg_len [nq, n_tables]
+ *             int32: its length, 0 = no such bucket.  Both come from the HOST: hashing stays in NumPy so that keys
+ *             match the reference bit for bit.
+ *   elem_off  [nq + 1] int64: exclusive prefix sum of a query's total bucket entries; m_total = elem_off[nq]
+ *             (< 2^31 per call: split large batches), max_per_query = the largest single total
+ *   cand      [nq, cap] int64 out, -1 = padding; cand_cnt [nq] int32 out (nullable): candidates found (<= cap)
+ * Two cub::DeviceRadixSort passes over 12 bytes per bucket entry; workspace from the _bytes query. */
+size_t vdb_lsh_candidates_workspace_bytes(int64_t m_total, int64_t nq);
+int vdb_lsh_candidates(const int32_t* tbl_ids, int64_t n_rows, const int64_t* seg_off, const int32_t* seg_len,
+                       const int64_t* elem_off, int64_t nq, int n_tables, int64_t m_total, int64_t max_per_query,
+                       int cap, int64_t* cand, int32_t* cand_cnt, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- IVF-Flat -------------------------------------------------------------------------- */
 /* Inverted lists, device layout ("interleaved-32"): list l occupies blocks
  * [blk_off[l], blk_off[l+1]) ; block b holds 32 vectors as float4 [d4][32 lanes]

@@ -219,6 +219,34 @@ def test_python_lsh_reference_kat_outputs(A):
     _check((g["kat_l2_D"], g["kat_l2_I"]), (d, i), atol=2e-6)
 
 
+@pytest.mark.parametrize("metric,params", [("cosine", dict(num_tables=8, hash_size=6)), ("cosine", dict(num_tables=12, hash_size=14)),
+                                           ("l2", dict(num_tables=10, hash_size=3, bucket_width=6.0)),
+                                           ("l2", dict(num_tables=4, hash_size=8, bucket_width=2.0))])
+@pytest.mark.parametrize("fallback", [True, False])
+def test_lsh_candidates_on_device_match_the_host_walk(A, metric, params, fallback):
+    """Device-side bucket union + vote order (vdb_lsh_candidates, two radix sorts) against the NumPy restatement of the
+    reference's Counter walk (src/algorithms/lsh.py:219-240): same candidates in the same most_common() order, hence
+    identical results - with duplicated rows (many votes), budgets above and below the union size, and queries that
+    hit no bucket at all."""
+    rng = np.random.RandomState(17)
+    base = rng.randn(30_000, 16).astype(np.float32)
+    base[200:260] = base[5]
+    queries = np.vstack([base[5:6], rng.randn(90, 16).astype(np.float32), 50.0 + rng.randn(3, 16).astype(np.float32)])
+    for mult in (2.0, 40.0, 4000.0):
+        got = {}
+        for mode in ("device", "host"):
+            algo = A.get_algorithm_instance("Composite", 16, name=f"lsh_{mode}", metric=metric,
+                                            indexer=dict(type="LSHIndexer", seed=9, **params),
+                                            searcher=dict(type="LSHSearcher", candidate_multiplier=mult, fallback_to_bruteforce=fallback,
+                                                          candidate_generation=mode))
+            algo.build_index(base)
+            assert (algo.searcher._csr_ids is not None) == (mode == "device")
+            got[mode] = algo.batch_search(queries, 10)
+        np.testing.assert_array_equal(got["device"][1], got["host"][1])
+        np.testing.assert_array_equal(got["device"][0], got["host"][0])
+    assert (got["device"][1][0, 0] == 5) and got["device"][1].shape == (94, 10)
+
+
 def test_lsh_self_retrieval_kats(A):
     """reference tests/test_composite_algorithm.py:108-166: identical vectors come back first with distance ~0."""
     rng = np.random.RandomState(7)

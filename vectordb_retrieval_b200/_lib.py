@@ -57,6 +57,8 @@ SIGNATURES = {
     "vdb_hamming_tc_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64]),
     "vdb_hamming_topk_tc": (_i32, [_p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "vdb_hamming_topk_tc_f16": (_i32, [_p, _p, _p, _i64, _p, _p, _i64, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
+    "vdb_lsh_candidates_workspace_bytes": (_sz, [_i64, _i64]),
+    "vdb_lsh_candidates": (_i32, [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "vdb_ivf_d4": (_i32, [_i32]),
     "vdb_ivf_count": (_i32, [_p, _i64, _i32, _p, _p]),
     "vdb_kmeans_accumulate": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p, _p]),

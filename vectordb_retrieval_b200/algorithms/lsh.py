@@ -74,6 +74,10 @@ class LSHIndexer(BaseIndexer):
             store = _normalize_rows(store)
 
         tables: List[Dict[Any, np.ndarray]] = []
+        # the same tables as flat arrays for the device-side candidate generation (vdb_lsh_candidates): per table the
+        # rows grouped by bucket (`ids`), and per bucket its (start, length) - looked up by key on the host
+        csr_ids = np.empty((self.num_tables, store.shape[0]), dtype=np.int32)
+        csr_slots: List[Any] = []
         proj = _project(store, projections)
         if self.metric == "cosine":
             keys = _cosine_keys(proj, bit_weights)                   # [n, T]
@@ -82,6 +86,8 @@ class LSHIndexer(BaseIndexer):
                 uniq, start = np.unique(keys[order, t], return_index=True)
                 stops = np.append(start[1:], order.size)
                 tables.append({int(k): order[a:b] for k, a, b in zip(uniq.tolist(), start.tolist(), stops.tolist())})
+                csr_ids[t] = order
+                csr_slots.append((uniq.astype(np.uint64), start.astype(np.int64), (stops - start).astype(np.int32)))
         else:
             codes = _l2_codes(proj, offsets, self.bucket_width)       # [n, T, H]
             for t in range(self.num_tables):
@@ -91,6 +97,8 @@ class LSHIndexer(BaseIndexer):
                 start = np.searchsorted(inverse[order], np.arange(uniq.shape[0]))
                 stops = np.append(start[1:], order.size)
                 tables.append({tuple(u): order[a:b] for u, a, b in zip(uniq.tolist(), start.tolist(), stops.tolist())})
+                csr_ids[t] = order
+                csr_slots.append({tuple(u): (a, b - a) for u, a, b in zip(uniq.tolist(), start.tolist(), stops.tolist())})
 
         meta: Dict[str, Any] = {"metric": self.metric, "num_tables": self.num_tables, "hash_size": self.hash_size}
         if self.metric == "cosine":
@@ -98,7 +106,7 @@ class LSHIndexer(BaseIndexer):
         else:
             meta["bucket_width"] = self.bucket_width
         data: Dict[str, Any] = {"tables": tables, "projections": projections, "vector_store": store,
-                                "bit_weights": bit_weights}
+                                "bit_weights": bit_weights, "csr_ids": csr_ids, "csr_slots": csr_slots}
         if offsets is not None:
             data["offsets"] = offsets
         return IndexArtifact(kind="lsh", data=data, metadata=meta)
@@ -141,10 +149,19 @@ class LSHSearcher(BaseSearcher):
         # the store is already normalised for cosine: score it as inner product, report 1 - score
         self._reranker = engine.Reranker(self.vector_store, "l2" if self.metric == "l2" else "ip", self.params.get("device"))
         self._flags = engine._lib.OUT_SQRT if self.metric == "l2" else engine._lib.OUT_ONE_MINUS
+        # candidate generation: "device" (bucket union + vote order by vdb_lsh_candidates) or "host" (the NumPy
+        # restatement of the reference's Counter walk; kept as the checker of the device path)
+        self.candidate_generation = str(self.params.get("candidate_generation", "device"))
+        self._csr_slots = data.get("csr_slots")
+        self._csr_ids = None
+        if self.candidate_generation == "device" and data.get("csr_ids") is not None and self.num_tables < 64:
+            import torch
+            self._csr_ids = torch.from_numpy(np.ascontiguousarray(data["csr_ids"], dtype=np.int32)).to(self._reranker.dev)
         self._prepared = True
 
     def memory_bytes(self) -> int:
         total = self._reranker.memory_bytes() if self._prepared else 0
+        total += self._csr_ids.numel() * 4 if getattr(self, "_csr_ids", None) is not None else 0
         return total + (self._flat.memory_bytes() if self._flat is not None else 0)
 
     # ---- host side: hashing, bucket lookup, vote ordering ------------------------------------
@@ -186,6 +203,8 @@ class LSHSearcher(BaseSearcher):
         q = self._prepare_queries(queries)
         nq = q.shape[0]
         cap = self._cap(k)
+        if self._csr_ids is not None:
+            return self._batch_search_device(q, k, cap)
         lists = [self._ordered_candidates(keys)[:cap] for keys in self._hash_queries(q)]
         empty = np.array([c.size == 0 for c in lists], dtype=bool)
         out_d = np.full((nq, k), np.inf, dtype=np.float32)
@@ -201,6 +220,81 @@ class LSHSearcher(BaseSearcher):
                 qd = engine.queries_to_device(q[rows], rr.dev, self.dimension)
                 d, i = engine.results_to_host(*rr.search(qd, torch.from_numpy(cand).to(rr.dev), k, self._flags, float("inf")))
                 out_d[rows], out_i[rows] = d, i
+            if empty.any() and self.fallback_to_bruteforce:          # no bucket hit: score every row (lsh.py:232-233)
+                if self._flat is None:
+                    self._flat = engine.FlatShard(self.vector_store, "l2" if self.metric == "l2" else "ip", rr.dev)
+                rows = np.nonzero(empty)[0]
+                qd = engine.queries_to_device(q[rows], rr.dev, self.dimension)
+                d, i = engine.results_to_host(*self._flat.search(qd, k, self._flags, float("inf")))
+                out_d[rows], out_i[rows] = d, i
+        return out_d, out_i
+
+    def _bucket_segments(self, q: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """(seg_off [nq, T] int64, seg_len [nq, T] int32): every query's bucket per table inside ``csr_ids``.
+        Hashing is the host's NumPy arithmetic (bit-identical keys); the lookup is a binary search per table for
+        the integer keys of the cosine hash, a dictionary lookup for the integer tuples of the L2 hash."""
+        nq, T, n = q.shape[0], self.num_tables, int(self._csr_ids.shape[1])
+        proj = _project(q, self.projections.reshape(T, self.hash_size, self.dimension))
+        seg_off = np.zeros((nq, T), dtype=np.int64)
+        seg_len = np.zeros((nq, T), dtype=np.int32)
+        if self.metric == "cosine":
+            keys = _cosine_keys(proj, self.bit_weights[: self.hash_size]).astype(np.uint64)          # [nq, T]
+            for t in range(T):
+                ukeys, starts, lens = self._csr_slots[t]
+                pos = np.minimum(np.searchsorted(ukeys, keys[:, t]), ukeys.shape[0] - 1)
+                hit = ukeys[pos] == keys[:, t]
+                seg_off[:, t] = t * n + starts[pos]
+                seg_len[:, t] = np.where(hit, lens[pos], 0)
+        else:
+            codes = _l2_codes(proj, self.offsets, self.bucket_width)
+            for t in range(T):
+                slots = self._csr_slots[t]
+                for r in range(nq):
+                    a, m = slots.get(tuple(codes[r, t].tolist()), (0, 0))
+                    seg_off[r, t], seg_len[r, t] = t * n + a, m
+        return seg_off, seg_len
+
+    def _batch_search_device(self, q: np.ndarray, k: int, cap: int, max_entries: int = 1 << 27) -> Tuple[np.ndarray, np.ndarray]:
+        """Candidate union, vote order, budget cut and rerank on the device; the host only hashes and looks buckets up."""
+        from .. import engine
+        import torch
+        lib, rr = engine._lib.load(), self._reranker
+        nq, T = q.shape[0], self.num_tables
+        seg_off, seg_len = self._bucket_segments(q)
+        per_query = seg_len.sum(axis=1, dtype=np.int64)
+        out_d = np.full((nq, k), np.inf, dtype=np.float32)
+        out_i = np.full((nq, k), -1, dtype=np.int64)
+        empty = per_query == 0
+        with torch.cuda.device(rr.dev):
+            lo = 0
+            while lo < nq:                                   # query chunks of at most `max_entries` bucket entries
+                hi = lo + 1
+                total = int(per_query[lo])
+                while hi < nq and total + int(per_query[hi]) <= max_entries:
+                    total += int(per_query[hi])
+                    hi += 1
+                if total >= (1 << 31):
+                    raise RuntimeError(f"one query unions {total} bucket entries; the device path handles < 2^31")
+                n_c = hi - lo
+                elem_off = np.zeros(n_c + 1, dtype=np.int64)
+                np.cumsum(per_query[lo:hi], out=elem_off[1:])
+                dev = rr.dev
+                so = torch.from_numpy(np.ascontiguousarray(seg_off[lo:hi])).to(dev)
+                sl = torch.from_numpy(np.ascontiguousarray(seg_len[lo:hi])).to(dev)
+                eo = torch.from_numpy(elem_off).to(dev)
+                cand = torch.empty((n_c, cap), dtype=torch.int64, device=dev)
+                ws = None
+                if total > 0:
+                    nbytes = lib.vdb_lsh_candidates_workspace_bytes(total, n_c)
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                engine.check(lib.vdb_lsh_candidates(engine.ptr(self._csr_ids), int(self._csr_ids.shape[1]), engine.ptr(so), engine.ptr(sl),
+                                                    engine.ptr(eo), n_c, T, total, int(per_query[lo:hi].max()), cap, engine.ptr(cand), None,
+                                                    engine.ptr(ws), 0 if ws is None else ws.numel(), engine._stream(dev)),
+                             "vdb_lsh_candidates")
+                qd = engine.queries_to_device(q[lo:hi], dev, self.dimension)
+                d, i = engine.results_to_host(*rr.search(qd, cand, k, self._flags, float("inf")))
+                out_d[lo:hi], out_i[lo:hi] = d, i
+                lo = hi
             if empty.any() and self.fallback_to_bruteforce:          # no bucket hit: score every row (lsh.py:232-233)
                 if self._flat is None:
                     self._flat = engine.FlatShard(self.vector_store, "l2" if self.metric == "l2" else "ip", rr.dev)
