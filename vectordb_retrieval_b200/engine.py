@@ -5,6 +5,7 @@ No arithmetic of the hot path is done in torch, and nothing falls back to the CP
 from __future__ import annotations
 
 import math
+import warnings
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -48,7 +49,10 @@ def to_device_f32(x, dev: torch.device, chunk_rows: int = 1 << 20) -> torch.Tens
     out = torch.empty((n, d), dtype=torch.float32, device=dev)
     for s in range(0, n, chunk_rows):
         blk = np.ascontiguousarray(x[s:s + chunk_rows], dtype=np.float32)
-        out[s:s + blk.shape[0]].copy_(torch.from_numpy(blk), non_blocking=False)
+        with warnings.catch_warnings():                    # a read-only memmap slice is only ever read from here
+            warnings.simplefilter("ignore", UserWarning)
+            src = torch.from_numpy(blk)
+        out[s:s + blk.shape[0]].copy_(src, non_blocking=False)
     return out
 
 
