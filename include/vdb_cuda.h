@@ -240,6 +240,30 @@ int vdb_ivf_scan_topk_ex(int metric, const float* list_vecs, const int32_t* list
                          float* out_d, int64_t* out_i, int64_t* scanned_rows,
                          int64_t rows_per_query_hint, void* stream);
 
+/* ---- IVF + 8-bit scalar quantiser ("IVF<n>,SQ8") ------------------------------------------------------------ */
+/* faiss.index_factory(d, "IVF<n>,SQ8") as reached from FaissFactoryIndexer (src/algorithms/modular.py:224-286;
+ * configs/benchmark_config.yaml:51-60): IndexIVFScalarQuantizer, QT_8bit, by_residual.  Coarse quantiser, k-means and
+ * assignment are the IVF-Flat ones (vdb_flat_topk over the centroids, vdb_kmeans_accumulate, vdb_ivf_count).
+ *   vdb_sq8_residuals  out[i,:] = x[i,:] - centroids[assign[i],:]             (training input of the quantiser)
+ *   vdb_sq8_train      vmin[j] = min_i r[i,j], vdiff[j] = max_i r[i,j] - vmin[j]; scratch = 2 * d uint32
+ *   vdb_sq8_fill       code = min(255, int(255 * clamp((r - vmin) / vdiff, 0, 1))) of the residual, scattered into the
+ *                      byte lists: block b holds 32 vectors as uint4 [d16][32 lanes], d16 = ceil(d / 16), byte c of slot
+ *                      v at ((b*d16 + c/16)*32 + v)*16 + c%16; blk_off / cursor / list_ids as for vdb_ivf_fill
+ *   vdb_ivf_sq8_scan_topk  decode r^ = vmin + vdiff * (code + 0.5) / 255 on the fly; L2: |q - c - r^|^2, inner product
+ *                      q.c + q.r^; top k per query, (distance, id) order; conventions and hint as vdb_ivf_scan_topk_ex */
+int vdb_sq8_d16(int d);
+int vdb_sq8_residuals(const float* x, int64_t n, int d, int64_t ld, const float* centroids, const int32_t* assign,
+                      float* out, void* stream);
+int vdb_sq8_train(const float* x, int64_t n, int d, int64_t ld, float* vmin, float* vdiff, void* scratch_2d_u32, void* stream);
+int vdb_sq8_fill(const float* x, int64_t n, int d, int64_t ld, const float* centroids, const int32_t* assign,
+                 const int32_t* blk_off, int nlist, int32_t* cursor, const float* vmin, const float* vdiff,
+                 uint8_t* list_codes, int32_t* list_ids, void* stream);
+int vdb_ivf_sq8_scan_topk(int metric, const uint8_t* list_codes, const int32_t* list_ids, const int32_t* blk_off,
+                          int nlist, int d, const float* centroids, const float* vmin, const float* vdiff,
+                          const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq,
+                          int k, int flags, float pad_value, int64_t id_offset, float* out_d, int64_t* out_i,
+                          int64_t rows_per_query_hint, void* stream);
+
 /* ---- Hamming top-k on the tensor pipe (large bases, nbits <= 256) ----------------------------- */
 /* Same contract as vdb_hamming_topk ((distance, id) order, out_d / out_i [nq,k] pre-filled by the
  * caller with padding), distances from a bf16 +-1 contraction on the tcgen05 pipeline of the flat

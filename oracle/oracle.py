@@ -17,7 +17,7 @@ Pinning status
   those files, the reference's own KATs (tests/test_composite_algorithm.py:29-226)
   and the published LSH recall 0.31914062499999996
   (benchmark_results/benchmark_20260305_070532/random/lsh_results.json:46).
-* FAISS paths (ExactSearch/IndexFlat values, IVF k-means, IndexLSH codes):
+* FAISS paths (ExactSearch/IndexFlat values, IVF k-means, IndexLSH codes, IVF-SQ8 ranges / codes):
   PARITY UNPINNED - faiss-cpu (requirements.txt:9, ``>=1.7.4``, no lock) is not in the
   reference tree and not installed.  ``faiss_flat_search`` / ``ivf_flat_search`` restate
   FAISS's documented conventions (squared L2 ascending, raw inner product descending,
@@ -517,6 +517,59 @@ def ivf_flat_search(base: np.ndarray, centroids: np.ndarray, assignments: np.nda
         out_d[r, :limit] = key[sel] if l2 else -key[sel]
         out_i[r, :limit] = ids[sel]
     return out_d, out_i, probes
+
+
+# --------------------------------------------------------------------------- IVF + 8-bit scalar quantiser
+def sq8_train(residuals: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """``ScalarQuantizer`` QT_8bit range training [FAISS-upstream: RS_minmax, rangestat_arg = 0]: per dimension
+    vmin = min, vdiff = max - min over the training residuals (reached from ``index.train`` of an
+    ``"IVF<n>,SQ8"`` index, src/algorithms/modular.py:277-283; configs/benchmark_config.yaml:51-60)."""
+    r = _as_f32(residuals)
+    vmin = r.min(axis=0)
+    return vmin, (r.max(axis=0) - vmin).astype(np.float32)
+
+
+def sq8_encode(residuals: np.ndarray, vmin: np.ndarray, vdiff: np.ndarray) -> np.ndarray:
+    """code = min(255, int(255 * clamp((r - vmin) / vdiff, 0, 1))) per component, fp32 arithmetic [FAISS-upstream Codec8bit]."""
+    r = _as_f32(residuals)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xi = np.where(vdiff != 0, (r - vmin[None, :]) / vdiff[None, :], np.float32(0.0)).astype(np.float32)
+    xi = np.clip(xi, np.float32(0.0), np.float32(1.0))
+    return np.minimum(255, (np.float32(255.0) * xi).astype(np.int32)).astype(np.uint8)
+
+
+def sq8_decode(codes: np.ndarray, vmin: np.ndarray, vdiff: np.ndarray) -> np.ndarray:
+    """r^ = vmin + vdiff * (code + 0.5) / 255 (fp64 here: the exact value the fp32 kernel approximates)."""
+    return vmin.astype(np.float64)[None, :] + vdiff.astype(np.float64)[None, :] * (codes.astype(np.float64) + 0.5) / 255.0
+
+
+def ivf_sq8_search(codes: np.ndarray, centroids: np.ndarray, assignments: np.ndarray, vmin: np.ndarray, vdiff: np.ndarray,
+                   queries: np.ndarray, k: int, nprobe: int, metric: str = "l2") -> Tuple[np.ndarray, np.ndarray]:
+    """``IndexIVFScalarQuantizer.search`` (by_residual) [FAISS-upstream] given the index's own centroids, assignments,
+    ranges and codes: per query the ``nprobe`` best lists, every row of those lists scored on its DECODED vector
+    c + r^ - squared L2 ascending / inner product descending, -1 / +-FLT_MAX padding (FAISS conventions)."""
+    q = _as_f32(np.atleast_2d(queries))
+    l2 = metric == "l2"
+    nlist = centroids.shape[0]
+    nprobe = min(nprobe, nlist)
+    _, probes = faiss_flat_search(centroids, q, nprobe, "l2" if l2 else "ip")
+    order = np.argsort(assignments, kind="stable")
+    counts = np.bincount(assignments, minlength=nlist)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    out_d = np.full((q.shape[0], k), FLT_MAX if l2 else -FLT_MAX, dtype=np.float32)
+    out_i = np.full((q.shape[0], k), -1, dtype=np.int64)
+    for r in range(q.shape[0]):
+        ids = np.concatenate([order[offsets[c]:offsets[c + 1]] for c in probes[r] if c >= 0])
+        if ids.size == 0:
+            continue
+        vec = centroids.astype(np.float64)[assignments[ids]] + sq8_decode(codes[ids], vmin, vdiff)
+        qq = q[r].astype(np.float64)
+        key = ((vec - qq) ** 2).sum(axis=1) if l2 else -(vec @ qq)
+        limit = min(k, ids.size)
+        sel = np.lexsort((ids, key))[:limit]
+        out_d[r, :limit] = key[sel] if l2 else -key[sel]
+        out_i[r, :limit] = ids[sel]
+    return out_d, out_i
 
 
 # --------------------------------------------------------------------------- IVF training (k-means recipe)

@@ -310,6 +310,25 @@ def test_ivf_pipeline_given_same_centroids_and_recall(A, metric):
         A.get_algorithm_instance("ApproximateSearch", 24, name="pq", index_type="IVF64,PQ8", metric="l2")
 
 
+def test_ivf_sq8_through_the_factory_indexer(A):
+    """configs/benchmark_config.yaml:51-60 of the reference: FaissFactoryIndexer(index_key="IVF256,SQ8") + FaissSearcher."""
+    rng = np.random.RandomState(8)
+    base = (rng.randn(40_000, 32) + 3.0 * rng.randn(64, 32)[rng.randint(0, 64, 40_000)]).astype(np.float32)
+    queries = base[rng.permutation(40_000)[:200]] + 0.05 * rng.randn(200, 32).astype(np.float32)
+    for metric in ("l2", "cosine"):
+        algo = A.get_algorithm_instance("Composite", 32, name="ivf_sq8", metric=metric,
+                                        indexer={"type": "FaissFactoryIndexer", "index_key": "IVF256,SQ8", "nprobe": 24},
+                                        searcher={"type": "FaissSearcher", "nprobe": 24})
+        algo.build_index(base)
+        assert type(algo.index_artifact.data).__name__ == "GpuIndexIVFSQ8" and algo.index_artifact.data.nprobe == 24
+        dist, idx = algo.batch_search(queries, 20)
+        assert dist.dtype == np.float32 and idx.dtype == np.int64 and dist.shape == (200, 20)
+        assert bool(np.all(np.diff(dist, axis=1) >= 0))                       # ascending: squared L2 / negated cosine
+        gt = oracle.linear_search(base, queries, 20, metric)[1]
+        assert oracle.recall_at_k(gt, idx, 10) > 0.9, oracle.recall_at_k(gt, idx, 10)
+        assert algo.get_memory_usage() < 40_000 * 32 * 4                      # one byte per component, not four
+
+
 def test_benchmark_runner_modular_end_to_end(A, tmp_path):
     """reference tests/test_benchmark_runner_modular.py:9-65: a tiny JSON config through
     BenchmarkRunner.run() with indexer_ref / searcher_ref resolution."""

@@ -237,6 +237,39 @@ def test_ivf_scan_matches_oracle_given_same_centroids(eng, metric):
     _check(ref, (D.cpu().numpy(), I.cpu().numpy()), atol=0.0 if m == "l2" else 1e-5)
 
 
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("n,d,nlist,k", [(30000, 50, 64, 100), (9000, 128, 32, 10), (5000, 7, 16, 200)])
+def test_ivf_sq8_matches_oracle_given_the_same_index(eng, metric, n, d, nlist, k):
+    """"IVF<n>,SQ8" (8-bit scalar-quantised residuals, by_residual): ranges and codes against the oracle's restatement of
+    the FAISS codec, then the list scan against the oracle GIVEN the device's centroids, assignments, ranges and codes,
+    for 1 / 2 / 4 / 8 warps per query."""
+    base, q = _data(n, d, 150, seed=n + d)
+    rng = np.random.RandomState(5)
+    cent = base[rng.permutation(n)[:nlist]].copy()
+    if metric == "cosine":
+        cent = oracle.safe_normalize(cent)
+    shard = eng.IVFSQ8Shard(base, cent, metric, "cuda")
+    b, qq = (oracle.safe_normalize(base), oracle.safe_normalize(q)) if metric == "cosine" else (base, q)
+    m = "l2" if metric == "l2" else "ip"
+    assign = shard.assign.cpu().numpy()
+    resid = b - cent[assign]
+    vmin, vdiff = oracle.sq8_train(resid)
+    np.testing.assert_array_equal(shard.vmin.cpu().numpy(), vmin)
+    np.testing.assert_allclose(shard.vdiff.cpu().numpy(), vdiff, rtol=1e-6)
+    codes = shard.codes_by_row()
+    ref_codes = oracle.sq8_encode(resid, shard.vmin.cpu().numpy(), shard.vdiff.cpu().numpy())
+    diff = codes.astype(np.int32) - ref_codes.astype(np.int32)
+    assert np.abs(diff).max() <= 1 and (diff != 0).mean() < 1e-3        # a component within rounding of a code boundary may flip
+    for nprobe in (1, 8, nlist // 2, nlist):
+        D, I = shard.search(torch.from_numpy(q.copy()).cuda(), k, nprobe, 0, oracle.FLT_MAX if m == "l2" else -oracle.FLT_MAX)
+        ref_d, ref_i = oracle.ivf_sq8_search(codes, cent, assign, shard.vmin.cpu().numpy(), shard.vdiff.cpu().numpy(), qq, k, nprobe, m)
+        scale = float(np.linalg.norm(b, axis=1).max() * np.linalg.norm(qq, axis=1).max())
+        _check((ref_d, ref_i), (D.cpu().numpy(), I.cpu().numpy()), rtol=2e-5, atol=2e-6 * scale)
+    # quantisation costs little recall against the exact search (nprobe = nlist scans every row)
+    exact = oracle.faiss_flat_search(b, qq, min(k, 10), m)
+    assert oracle.recall_at_k(exact[1], I.cpu().numpy()[:, : min(k, 10)], min(k, 10)) > 0.85
+
+
 def test_row_utilities(eng):
     base, _ = _data(1000, 50, 1, seed=4)
     base[3] = 0

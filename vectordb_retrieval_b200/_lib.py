@@ -67,6 +67,12 @@ SIGNATURES = {
                                  _p, _p, _p, _p]),
     "vdb_ivf_scan_topk_ex": (_i32, [_i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
                                     _p, _p, _p, _i64, _p]),
+    "vdb_sq8_d16": (_i32, [_i32]),
+    "vdb_sq8_residuals": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
+    "vdb_sq8_train": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
+    "vdb_sq8_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "vdb_ivf_sq8_scan_topk": (_i32, [_i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
+                                     _p, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -139,10 +139,10 @@ class FaissFactoryIndexer(BaseIndexer):
     _RUNTIME_PARAM_KEYS = ("nprobe",)                                      # search-time attributes (modular.py:269-275)
 
     def __init__(self, name: str, dimension: int, metric: str = "l2", index_key: str = "Flat", **kwargs: Any) -> None:
-        from ..indexes import _IVF_FLAT
-        if index_key.strip() != "Flat" and not _IVF_FLAT.match(index_key.strip()):
+        from ..indexes import _IVF_FLAT, _IVF_SQ8
+        if index_key.strip() != "Flat" and not _IVF_FLAT.match(index_key.strip()) and not _IVF_SQ8.match(index_key.strip()):
             raise ValueError(f"index_key '{index_key}' is not supported by the CUDA build "
-                             "(supported: 'Flat', 'IVF<nlist>,Flat')")
+                             "(supported: 'Flat', 'IVF<nlist>,Flat', 'IVF<nlist>,SQ8')")
         self.index_key = index_key
         params = dict(kwargs)
         params.setdefault("index_key", index_key)

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvdbcuda.so")
-SOURCES = ["prep.cu", "flat.cu", "rerank.cu", "ivf.cu", "lsh.cu", "lsh_cand.cu"]
+SOURCES = ["prep.cu", "flat.cu", "rerank.cu", "ivf.cu", "lsh.cu", "lsh_cand.cu", "sq8.cu"]
 HEADERS = ["common.cuh", "ptx_sm100.cuh", "flat_tc.cuh", "select.cuh", os.path.join("..", "..", "include", "vdb_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -50,10 +50,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    tmp = LIB + ".linking"                       # link beside the target, then rename: a reader never sees a partial library
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     return LIB
 
 

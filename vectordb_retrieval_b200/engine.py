@@ -470,6 +470,91 @@ class IVFShard:
         return out_d, out_i
 
 
+class IVFSQ8Shard:
+    """``IVF<nlist>,SQ8`` of one GPU's rows: the IVF-Flat coarse quantiser plus inverted lists of 8-bit codes of the
+    residuals x - centroid (FAISS ``IndexIVFScalarQuantizer``, QT_8bit, by_residual) in the interleaved-32 byte layout.
+    HBM: d bytes per row instead of 4 d."""
+
+    def __init__(self, vectors, centroids, metric: str = "l2", device=None, id_offset: int = 0, assign_batch: int = 1 << 18):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.id_offset = int(id_offset)
+        base = to_device_f32(vectors, self.dev)
+        if metric == "cosine":
+            base = normalized_rows(base)
+        self.n, self.d = base.shape
+        cent = to_device_f32(centroids, self.dev)
+        self.nlist = cent.shape[0]
+        self.quantizer = FlatShard(cent, "l2" if metric == "l2" else "ip", self.dev)
+        self.centroids = cent
+        s = _stream(self.dev)
+        with torch.cuda.device(self.dev):
+            assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
+            for a in range(0, self.n, assign_batch):
+                _, idx = self.quantizer.search(base[a:a + assign_batch], 1)
+                assign[a:a + assign_batch] = idx[:, 0].to(torch.int32)
+            self.assign = assign
+            # the quantiser's ranges come from the residuals of every row handed to train/add (the reference trains on the base)
+            resid = torch.empty((self.n, self.d), dtype=torch.float32, device=self.dev)
+            check(self.lib.vdb_sq8_residuals(ptr(base), self.n, self.d, base.stride(0), ptr(cent), ptr(assign), ptr(resid), s),
+                  "vdb_sq8_residuals")
+            self.vmin = torch.empty(self.d, dtype=torch.float32, device=self.dev)
+            self.vdiff = torch.empty(self.d, dtype=torch.float32, device=self.dev)
+            scratch = torch.empty(2 * self.d, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_sq8_train(ptr(resid), self.n, self.d, resid.stride(0), ptr(self.vmin), ptr(self.vdiff), ptr(scratch), s),
+                  "vdb_sq8_train")
+            del resid
+            counts = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_ivf_count(ptr(assign), self.n, self.nlist, ptr(counts), s), "vdb_ivf_count")
+            blocks = (counts.to(torch.int64) + 31) // 32
+            blk_off = torch.zeros(self.nlist + 1, dtype=torch.int32, device=self.dev)
+            blk_off[1:] = torch.cumsum(blocks, 0).to(torch.int32)
+            n_blocks = int(blk_off[-1].item())
+            self.d16 = self.lib.vdb_sq8_d16(self.d)
+            self.list_codes = torch.zeros(max(n_blocks, 1) * self.d16 * 32 * 16, dtype=torch.uint8, device=self.dev)
+            self.list_ids = torch.full((max(n_blocks, 1) * 32,), -1, dtype=torch.int32, device=self.dev)
+            cursor = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_sq8_fill(ptr(base), self.n, self.d, base.stride(0), ptr(cent), ptr(assign), ptr(blk_off), self.nlist,
+                                        ptr(cursor), ptr(self.vmin), ptr(self.vdiff), ptr(self.list_codes), ptr(self.list_ids), s),
+                  "vdb_sq8_fill")
+            self.blk_off, self.counts, self.n_blocks = blk_off, counts, n_blocks
+            torch.cuda.current_stream(self.dev).synchronize()
+
+    def memory_bytes(self) -> int:
+        return self.list_codes.numel() + self.list_ids.numel() * 4 + self.quantizer.memory_bytes() + 8 * self.d
+
+    def codes_by_row(self) -> np.ndarray:
+        """[n, d] uint8 codes in row order (test hook: undoes the interleaved list layout on the host)."""
+        ids = self.list_ids.cpu().numpy()
+        raw = self.list_codes.cpu().numpy().reshape(-1, self.d16, 32, 16)            # [block, chunk, slot, byte]
+        per_slot = raw.transpose(0, 2, 1, 3).reshape(-1, self.d16 * 16)[:, : self.d]    # [block * 32 slots, d]
+        out = np.zeros((self.n, self.d), dtype=np.uint8)
+        live = ids >= 0
+        out[ids[live]] = per_slot[live]
+        return out
+
+    def search(self, q: torch.Tensor, k: int, nprobe: int, flags: int = 0, pad_value: float = FLT_MAX
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        nq = q.shape[0]
+        nprobe = max(1, min(int(nprobe), self.nlist))
+        if nprobe > MAX_FLAT_K:
+            raise RuntimeError(f"nprobe={nprobe} is not supported: the coarse quantiser selects at most {MAX_FLAT_K} lists per query")
+        with torch.cuda.device(self.dev):
+            if self.metric == "cosine":
+                q = normalized_rows(q)
+            _, probes = self.quantizer.search(q, nprobe)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
+            rows_hint = max(1, nprobe * self.n // max(self.nlist, 1))
+            check(self.lib.vdb_ivf_sq8_scan_topk(metric_code(self.metric), ptr(self.list_codes), ptr(self.list_ids), ptr(self.blk_off),
+                                                 self.nlist, self.d, ptr(self.centroids), ptr(self.vmin), ptr(self.vdiff), ptr(probes),
+                                                 nprobe, ptr(q), q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d),
+                                                 ptr(out_i), rows_hint, _stream(self.dev)), "vdb_ivf_sq8_scan_topk")
+        self.last_probes = probes
+        return out_d, out_i
+
+
 class HammingShard:
     """Sign-projection codes of one GPU's rows + the Hamming top-k scan (``faiss.IndexLSH``).
 

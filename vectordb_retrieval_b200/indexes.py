@@ -193,6 +193,26 @@ class GpuIndexIVFFlat:
             return engine.results_to_host(*self.search_device(q, int(k)))
 
 
+class GpuIndexIVFSQ8(GpuIndexIVFFlat):
+    """``faiss.index_factory(d, "IVF<nlist>,SQ8", metric)``: the IVF-Flat coarse quantiser with inverted lists of 8-bit
+    scalar-quantised residuals (FAISS ``IndexIVFScalarQuantizer``, QT_8bit, by_residual; value conventions of FAISS:
+    squared L2 ascending / inner product descending, of the DECODED vectors).  Persistence is not implemented."""
+
+    def add(self, x) -> None:
+        if not self.is_trained:
+            raise RuntimeError("GpuIndexIVFSQ8.add before train")
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexIVFSQ8.add may be called once")
+        self._impl = engine.IVFSQ8Shard(x, self.centroids, self._engine_metric(), self.device)
+        self.ntotal = int(x.shape[0])
+
+    def save(self, artifact_dir: str, context=None):
+        raise NotImplementedError("GpuIndexIVFSQ8 does not support index persistence")
+
+    def load(self, artifact_dir: str, context=None):
+        raise NotImplementedError("GpuIndexIVFSQ8 does not support index persistence")
+
+
 class GpuIndexLSH:
     """``faiss.IndexLSH(d, nbits)``: sign bits of a random projection, Hamming top-k.
 
@@ -262,11 +282,12 @@ class GpuIndexLSH:
 
 
 _IVF_FLAT = re.compile(r"^IVF(\d+),Flat$")
+_IVF_SQ8 = re.compile(r"^IVF(\d+),SQ8$")
 
 
 def index_factory(d: int, key: str, metric="l2", **kwargs):
     """The subset of ``faiss.index_factory`` grammar that reaches the scan + top-k path:
-    ``"Flat"``, ``"IVF<nlist>,Flat"`` and ``"LSH"``.  Anything else (PQ, SQ, HNSW, ...) is outside
+    ``"Flat"``, ``"IVF<nlist>,Flat"``, ``"IVF<nlist>,SQ8"`` and ``"LSH"``.  Anything else (PQ, HNSW, ...) is outside
     this build (out of scope) and raises ValueError at construction time."""
     key = key.strip()
     if key == "Flat":
@@ -274,6 +295,9 @@ def index_factory(d: int, key: str, metric="l2", **kwargs):
     m = _IVF_FLAT.match(key)
     if m:
         return GpuIndexIVFFlat(d, int(m.group(1)), metric, **kwargs)
+    m = _IVF_SQ8.match(key)
+    if m:
+        return GpuIndexIVFSQ8(d, int(m.group(1)), metric, **kwargs)
     if key == "LSH":
         return GpuIndexLSH(d, kwargs.pop("nbits", 256), **kwargs)
-    raise ValueError(f"index key '{key}' is not supported by the CUDA build (supported: 'Flat', 'IVF<n>,Flat', 'LSH')")
+    raise ValueError(f"index key '{key}' is not supported by the CUDA build (supported: 'Flat', 'IVF<n>,Flat', 'IVF<n>,SQ8', 'LSH')")
