@@ -80,6 +80,28 @@ def main() -> int:
                           "algorithmic_gb": rows * d * 4 / 1e9, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}), flush=True)
     del ivf, shard
 
+    # IVF<nlist>,SQ8: the same coarse quantiser, 8-bit residual codes (one byte per component in the lists)
+    t0 = time.time()
+    sq = indexes.GpuIndexIVFSQ8(d, args.nlist, "ip", device=dev, normalize=True)
+    sq.train(base)
+    sq.add(base)
+    torch.cuda.synchronize()
+    print(json.dumps({"algo": "ivf_sq8_build", "nlist": args.nlist, "train_plus_add_s": time.time() - t0,
+                      "list_bytes_per_row": int(sq._impl.d16 * 16)}), flush=True)
+    shard = sq._impl
+    for nprobe in (1, 8, 32, 128):
+        pad = -engine.FLT_MAX
+        ms_total, (D, I) = timed(lambda: shard.search(q_dev.clone(), k, nprobe, 0, pad))
+        qn = engine.normalize_rows_(q_dev.clone())
+        ms_coarse, _ = timed(lambda: shard.quantizer.search(qn.clone(), nprobe))
+        ms_scan = max(ms_total - ms_coarse, 1e-3)
+        rows = nprobe * args.n / args.nlist * args.nq            # expected scanned rows (lists are balanced to within the k-means)
+        gbs = rows * shard.d16 * 16 / (ms_scan * 1e-3) / 1e9
+        print(json.dumps({"algo": "ivf_sq8", "nprobe": nprobe, "recall@100": recall_at_k(gt, I.cpu().numpy(), 100), "ms_total": ms_total,
+                          "ms_coarse": ms_coarse, "ms_list_scan": ms_scan, "qps": args.nq / ms_total * 1e3,
+                          "approx_code_gb": rows * shard.d16 * 16 / 1e9, "approx_code_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}), flush=True)
+    del sq, shard
+
     lsh = indexes.GpuIndexLSH(d, 256, device=dev)
     lsh.add(base)
     rr = engine.Reranker(base, "cosine", dev)
