@@ -17,7 +17,7 @@ Pinning status
   those files, the reference's own KATs (tests/test_composite_algorithm.py:29-226)
   and the published LSH recall 0.31914062499999996
   (benchmark_results/benchmark_20260305_070532/random/lsh_results.json:46).
-* FAISS paths (ExactSearch/IndexFlat values, IVF k-means, IndexLSH codes, IVF-SQ8 ranges / codes):
+* FAISS paths (ExactSearch/IndexFlat values, IVF k-means, IndexLSH codes, IVF-SQ8 ranges / codes, PQ codebooks / codes):
   PARITY UNPINNED - faiss-cpu (requirements.txt:9, ``>=1.7.4``, no lock) is not in the
   reference tree and not installed.  ``faiss_flat_search`` / ``ivf_flat_search`` restate
   FAISS's documented conventions (squared L2 ascending, raw inner product descending,
@@ -565,6 +565,63 @@ def ivf_sq8_search(codes: np.ndarray, centroids: np.ndarray, assignments: np.nda
         vec = centroids.astype(np.float64)[assignments[ids]] + sq8_decode(codes[ids], vmin, vdiff)
         qq = q[r].astype(np.float64)
         key = ((vec - qq) ** 2).sum(axis=1) if l2 else -(vec @ qq)
+        limit = min(k, ids.size)
+        sel = np.lexsort((ids, key))[:limit]
+        out_d[r, :limit] = key[sel] if l2 else -key[sel]
+        out_i[r, :limit] = ids[sel]
+    return out_d, out_i
+
+
+# --------------------------------------------------------------------------- product quantisation
+def pq_encode(x: np.ndarray, codebooks: np.ndarray) -> np.ndarray:
+    """``ProductQuantizer::compute_codes`` [FAISS-upstream]: per sub-space the nearest of its 256 centroids (squared L2,
+    ties to the lowest index), fp64.  ``codebooks`` [M, 256, dsub]; returns codes [n, M] uint8.  Reached from ``index.add`` of
+    a ``"PQ<m>"`` / ``"IVF<n>,PQ<m>"`` index (src/algorithms/modular.py:277-283; configs/benchmark_config.yaml:36-50,61-72)."""
+    x = np.asarray(x, dtype=np.float64)
+    m, _, dsub = codebooks.shape
+    codes = np.empty((x.shape[0], m), dtype=np.uint8)
+    for s in range(m):
+        sub = x[:, s * dsub:(s + 1) * dsub]
+        cb = codebooks[s].astype(np.float64)
+        d2 = (sub ** 2).sum(axis=1)[:, None] - 2.0 * sub @ cb.T + (cb ** 2).sum(axis=1)[None, :]
+        codes[:, s] = np.argmin(d2, axis=1)
+    return codes
+
+
+def pq_decode(codes: np.ndarray, codebooks: np.ndarray) -> np.ndarray:
+    """Reconstruction: the concatenation of the selected sub-centroids, fp64 [n, d]."""
+    m = codebooks.shape[0]
+    return np.concatenate([codebooks[s].astype(np.float64)[codes[:, s]] for s in range(m)], axis=1)
+
+
+def ivf_pq_search(codes: np.ndarray, centroids: Optional[np.ndarray], assignments: np.ndarray, codebooks: np.ndarray,
+                  queries: np.ndarray, k: int, nprobe: int, metric: str = "l2") -> Tuple[np.ndarray, np.ndarray]:
+    """``IndexIVFPQ.search`` (by_residual) - or ``IndexPQ.search`` when ``centroids`` is None - [FAISS-upstream] given the
+    index's own centroids, assignments, codebooks and codes: every row of the probed lists scored on its RECONSTRUCTED
+    vector c + decode(code) (what the look-up-table sum equals); FAISS value conventions."""
+    q = _as_f32(np.atleast_2d(queries))
+    l2 = metric == "l2"
+    n = codes.shape[0]
+    recon = pq_decode(codes, codebooks)
+    if centroids is None:
+        probes = np.zeros((q.shape[0], 1), dtype=np.int64)
+        assignments = np.zeros(n, dtype=np.int64)
+        nlist = 1
+    else:
+        nlist = centroids.shape[0]
+        _, probes = faiss_flat_search(centroids, q, min(nprobe, nlist), "l2" if l2 else "ip")
+        recon = recon + centroids.astype(np.float64)[assignments]
+    order = np.argsort(assignments, kind="stable")
+    counts = np.bincount(assignments, minlength=nlist)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    out_d = np.full((q.shape[0], k), FLT_MAX if l2 else -FLT_MAX, dtype=np.float32)
+    out_i = np.full((q.shape[0], k), -1, dtype=np.int64)
+    for r in range(q.shape[0]):
+        ids = np.concatenate([order[offsets[c]:offsets[c + 1]] for c in probes[r] if c >= 0])
+        if ids.size == 0:
+            continue
+        qq = q[r].astype(np.float64)
+        key = ((recon[ids] - qq) ** 2).sum(axis=1) if l2 else -(recon[ids] @ qq)
         limit = min(k, ids.size)
         sel = np.lexsort((ids, key))[:limit]
         out_d[r, :limit] = key[sel] if l2 else -key[sel]

@@ -329,6 +329,29 @@ def test_ivf_sq8_through_the_factory_indexer(A):
         assert algo.get_memory_usage() < 40_000 * 32 * 4                      # one byte per component, not four
 
 
+@pytest.mark.parametrize("index_key,min_recall", [("IVF256,PQ32", 0.55), ("PQ32", 0.55), ("IVF256,PQ8", 0.2)])
+def test_product_quantiser_indexes_through_the_factory_indexer(A, index_key, min_recall):
+    """configs/benchmark_config.yaml:36-50,61-72 of the reference: FaissFactoryIndexer(index_key="IVF256,PQ64" | "PQ64") +
+    FaissSearcher.  Codes are lossy: the check is the contract (shapes, order, conventions) and a recall floor."""
+    rng = np.random.RandomState(8)
+    base = (rng.randn(40_000, 32) + 3.0 * rng.randn(64, 32)[rng.randint(0, 64, 40_000)]).astype(np.float32)
+    queries = base[rng.permutation(40_000)[:200]] + 0.05 * rng.randn(200, 32).astype(np.float32)
+    for metric in ("l2", "cosine"):
+        algo = A.get_algorithm_instance("Composite", 32, name="pq", metric=metric,
+                                        indexer={"type": "FaissFactoryIndexer", "index_key": index_key, "nprobe": 24},
+                                        searcher={"type": "FaissSearcher", "nprobe": 24})
+        algo.build_index(base)
+        dist, idx = algo.batch_search(queries, 20)
+        assert dist.dtype == np.float32 and idx.dtype == np.int64 and dist.shape == (200, 20)
+        assert bool(np.all(np.diff(dist, axis=1) >= 0)) and int(idx.min()) >= 0 and int(idx.max()) < 40_000
+        gt = oracle.linear_search(base, queries, 20, metric)[1]
+        rec = oracle.recall_at_k(gt, idx, 10)
+        assert rec > min_recall, (index_key, metric, rec)
+    with pytest.raises(ValueError):
+        A.get_algorithm_instance("Composite", 30, name="bad", metric="l2", indexer={"type": "FaissFactoryIndexer", "index_key": "PQ8"},
+                                 searcher={"type": "FaissSearcher"}).build_index(base[:, :30])
+
+
 def test_benchmark_runner_modular_end_to_end(A, tmp_path):
     """reference tests/test_benchmark_runner_modular.py:9-65: a tiny JSON config through
     BenchmarkRunner.run() with indexer_ref / searcher_ref resolution."""

@@ -274,6 +274,44 @@ def test_ivf_sq8_matches_oracle_given_the_same_index(eng, metric, n, d, nlist, k
     assert oracle.recall_at_k(exact[1], I.cpu().numpy()[:, : min(k, 10)], min(k, 10)) > 0.85
 
 
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+@pytest.mark.parametrize("n,d,m,nlist,k", [(20000, 64, 64, 32, 100), (12000, 48, 8, 16, 10), (9000, 50, 50, 0, 20), (6000, 96, 16, 0, 200)])
+def test_pq_matches_oracle_given_the_same_index(eng, metric, n, d, m, nlist, k):
+    """"IVF<n>,PQ<m>" (nlist > 0) and "PQ<m>" (nlist = 0): codes against the oracle's encoder given the device's
+    codebooks, then the look-up-table scan against the oracle scoring the RECONSTRUCTED vectors, given the device's
+    centroids, assignments, codebooks and codes."""
+    base, q = _data(n, d, 120, seed=n + d + m)
+    rng = np.random.RandomState(6)
+    cent = None
+    if nlist:
+        cent = base[rng.permutation(n)[:nlist]].copy()
+        if metric == "cosine":
+            cent = oracle.safe_normalize(cent)
+    shard = eng.IVFPQShard(base, cent, m, metric, "cuda", niter=4)
+    b, qq = (oracle.safe_normalize(base), oracle.safe_normalize(q)) if metric == "cosine" else (base, q)
+    mm = "l2" if metric == "l2" else "ip"
+    books = shard.codebooks.cpu().numpy()
+    assert books.shape == (m, 256, d // m) and np.isfinite(books).all()
+    assign = shard.assign.cpu().numpy().astype(np.int64)
+    resid = b - cent[assign] if nlist else b
+    codes = shard.codes.cpu().numpy()
+    ref_codes = oracle.pq_encode(resid, books)
+    differ = codes != ref_codes
+    assert differ.mean() < 2e-3, differ.mean()              # near-ties between two sub-centroids (fp32 vs fp64) only
+    if differ.any():                                        # ... and where they differ the two choices are equally good
+        rr, ss = np.nonzero(differ)
+        dsub = d // m
+        sub = np.stack([resid[r, s_ * dsub:(s_ + 1) * dsub] for r, s_ in zip(rr, ss)]).astype(np.float64)
+        da = ((sub - books[ss, codes[rr, ss]].astype(np.float64)) ** 2).sum(1)
+        db = ((sub - books[ss, ref_codes[rr, ss]].astype(np.float64)) ** 2).sum(1)
+        np.testing.assert_allclose(da, db, rtol=1e-4, atol=1e-6)
+    for nprobe in ((1, 4, nlist) if nlist else (1,)):
+        D, I = shard.search(torch.from_numpy(q.copy()).cuda(), k, nprobe, 0, oracle.FLT_MAX if mm == "l2" else -oracle.FLT_MAX)
+        ref_d, ref_i = oracle.ivf_pq_search(codes, cent, assign, books, qq, k, nprobe, mm)
+        scale = float(np.linalg.norm(b, axis=1).max() * np.linalg.norm(qq, axis=1).max())
+        _check((ref_d, ref_i), (D.cpu().numpy(), I.cpu().numpy()), rtol=2e-5, atol=2e-6 * scale)
+
+
 def test_row_utilities(eng):
     base, _ = _data(1000, 50, 1, seed=4)
     base[3] = 0

@@ -22,7 +22,7 @@ def test_registries_mirror_reference_type_names():
     with pytest.raises(ValueError):
         A.get_indexer_class("HNSWIndexer")
     with pytest.raises(ValueError):
-        A.FaissFactoryIndexer("x", 8, index_key="IVF16,PQ4")
+        A.FaissFactoryIndexer("x", 8, index_key="IVF16,HNSW32")      # graph indexes stay outside the build; PQ / SQ8 are in
     with pytest.raises(ValueError):
         A.LSHIndexer("x", 8, metric="ip")
     with pytest.raises(ValueError):

@@ -139,10 +139,11 @@ class FaissFactoryIndexer(BaseIndexer):
     _RUNTIME_PARAM_KEYS = ("nprobe",)                                      # search-time attributes (modular.py:269-275)
 
     def __init__(self, name: str, dimension: int, metric: str = "l2", index_key: str = "Flat", **kwargs: Any) -> None:
-        from ..indexes import _IVF_FLAT, _IVF_SQ8
-        if index_key.strip() != "Flat" and not _IVF_FLAT.match(index_key.strip()) and not _IVF_SQ8.match(index_key.strip()):
+        from ..indexes import _IVF_FLAT, _IVF_PQ, _IVF_SQ8, _PQ
+        key = index_key.strip()
+        if key != "Flat" and not any(rx.match(key) for rx in (_IVF_FLAT, _IVF_SQ8, _IVF_PQ, _PQ)):
             raise ValueError(f"index_key '{index_key}' is not supported by the CUDA build "
-                             "(supported: 'Flat', 'IVF<nlist>,Flat', 'IVF<nlist>,SQ8')")
+                             "(supported: 'Flat', 'IVF<nlist>,Flat', 'IVF<nlist>,SQ8', 'IVF<nlist>,PQ<m>', 'PQ<m>')")
         self.index_key = index_key
         params = dict(kwargs)
         params.setdefault("index_key", index_key)
@@ -161,7 +162,7 @@ class FaissFactoryIndexer(BaseIndexer):
             kind = "ip"
             meta["faiss_metric"] = "ip"
         train_kwargs = {key: self.params[key] for key in self._TRAIN_PARAM_KEYS
-                        if key in self.params and self.index_key.strip() != "Flat"}
+                        if key in self.params and self.index_key.strip().startswith("IVF")}
         index = index_factory(self.dimension, self.index_key, kind, device=self.params.get("device"), normalize=normalize,
                               **train_kwargs)
         meta.update(train_kwargs)

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvdbcuda.so")
-SOURCES = ["prep.cu", "flat.cu", "rerank.cu", "ivf.cu", "lsh.cu", "lsh_cand.cu", "sq8.cu"]
+SOURCES = ["prep.cu", "flat.cu", "rerank.cu", "ivf.cu", "lsh.cu", "lsh_cand.cu", "sq8.cu", "pq.cu"]
 HEADERS = ["common.cuh", "ptx_sm100.cuh", "flat_tc.cuh", "select.cuh", os.path.join("..", "..", "include", "vdb_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

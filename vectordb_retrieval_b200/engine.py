@@ -555,6 +555,115 @@ class IVFSQ8Shard:
         return out_d, out_i
 
 
+def pq_train(residuals: torch.Tensor, m: int, niter: int = 25, seed: int = 1234, max_points_per_centroid: int = 256) -> np.ndarray:
+    """Codebooks [m, 256, d / m] of a product quantiser: the IVF k-means recipe (``kmeans_train``) run per sub-space on at
+    most 256 * 256 sampled rows, 25 iterations (FAISS ``ProductQuantizer::train`` [FAISS-upstream]; its RNG is not
+    reproduced - parity is defined given the codebooks)."""
+    n, d = int(residuals.shape[0]), int(residuals.shape[1])
+    if d % m != 0:
+        raise RuntimeError(f"the dimension {d} is not a multiple of the {m} sub-quantisers")
+    if n < 256:
+        raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters (256)")
+    dsub = d // m
+    limit = max_points_per_centroid * 256
+    if n > limit:
+        pick = np.sort(np.random.RandomState(seed).choice(n, limit, replace=False))
+        sample = residuals[torch.from_numpy(pick).to(residuals.device)].cpu().numpy()
+    else:
+        sample = residuals.cpu().numpy()
+    books = np.empty((m, 256, dsub), dtype=np.float32)
+    for s in range(m):
+        books[s] = kmeans_train(sample[:, s * dsub:(s + 1) * dsub], 256, "l2", residuals.device, niter=niter, seed=seed + 1 + s,
+                                max_points_per_centroid=max_points_per_centroid)
+    return books
+
+
+class IVFPQShard:
+    """``IVF<nlist>,PQ<m>`` (``centroids`` given) or ``PQ<m>`` (``centroids=None``: one list, zero centroid) of one GPU's
+    rows: m code bytes per row - the nearest of 256 sub-centroids per sub-space of the residual x - centroid - in the
+    interleaved-32 byte lists; search builds a look-up table per (query, probed list) in shared memory."""
+
+    def __init__(self, vectors, centroids, m: int, metric: str = "l2", device=None, id_offset: int = 0, codebooks=None,
+                 niter: int = 25, seed: int = 1234, assign_batch: int = 1 << 18):
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.id_offset = int(id_offset)
+        self.m = int(m)
+        base = to_device_f32(vectors, self.dev)
+        if metric == "cosine":
+            base = normalized_rows(base)
+        self.n, self.d = base.shape
+        if self.d % self.m != 0:
+            raise RuntimeError(f"the dimension {self.d} is not a multiple of the {self.m} sub-quantisers")
+        s = _stream(self.dev)
+        with torch.cuda.device(self.dev):
+            if centroids is None:
+                self.nlist, self.centroids, self.quantizer = 1, None, None
+                assign = torch.zeros(self.n, dtype=torch.int32, device=self.dev)
+                resid = base
+            else:
+                cent = to_device_f32(centroids, self.dev)
+                self.nlist, self.centroids = cent.shape[0], cent
+                self.quantizer = FlatShard(cent, "l2" if metric == "l2" else "ip", self.dev)
+                assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
+                for a in range(0, self.n, assign_batch):
+                    _, idx = self.quantizer.search(base[a:a + assign_batch], 1)
+                    assign[a:a + assign_batch] = idx[:, 0].to(torch.int32)
+                resid = torch.empty((self.n, self.d), dtype=torch.float32, device=self.dev)
+                check(self.lib.vdb_sq8_residuals(ptr(base), self.n, self.d, base.stride(0), ptr(cent), ptr(assign), ptr(resid), s),
+                      "vdb_sq8_residuals")
+            self.assign = assign
+            books = pq_train(resid, self.m, niter=niter, seed=seed) if codebooks is None else np.ascontiguousarray(codebooks, dtype=np.float32)
+            if books.shape != (self.m, 256, self.d // self.m):
+                raise RuntimeError(f"codebooks have shape {books.shape}, expected {(self.m, 256, self.d // self.m)}")
+            self.codebooks = torch.from_numpy(books).to(self.dev)
+            codes = torch.empty((self.n, self.m), dtype=torch.uint8, device=self.dev)
+            check(self.lib.vdb_pq_encode(ptr(resid), self.n, self.d, resid.stride(0), ptr(self.codebooks), self.m, ptr(codes), s),
+                  "vdb_pq_encode")
+            self.codes = codes                                   # [n, m] in row order (kept: 1/4..1/32 of the fp32 rows)
+            counts = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_ivf_count(ptr(assign), self.n, self.nlist, ptr(counts), s), "vdb_ivf_count")
+            blocks = (counts.to(torch.int64) + 31) // 32
+            blk_off = torch.zeros(self.nlist + 1, dtype=torch.int32, device=self.dev)
+            blk_off[1:] = torch.cumsum(blocks, 0).to(torch.int32)
+            n_blocks = int(blk_off[-1].item())
+            self.m16 = self.lib.vdb_sq8_d16(self.m)
+            self.lists = torch.zeros(max(n_blocks, 1) * self.m16 * 32 * 16, dtype=torch.uint8, device=self.dev)
+            self.list_ids = torch.full((max(n_blocks, 1) * 32,), -1, dtype=torch.int32, device=self.dev)
+            cursor = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            check(self.lib.vdb_bytes_fill(ptr(codes), self.n, self.m, ptr(assign), ptr(blk_off), self.nlist, ptr(cursor),
+                                          ptr(self.lists), ptr(self.list_ids), s), "vdb_bytes_fill")
+            self.blk_off, self.counts = blk_off, counts
+            torch.cuda.current_stream(self.dev).synchronize()
+
+    def memory_bytes(self) -> int:
+        q = self.quantizer.memory_bytes() if self.quantizer is not None else 0
+        return self.lists.numel() + self.list_ids.numel() * 4 + self.codes.numel() + self.codebooks.numel() * 4 + q
+
+    def search(self, q: torch.Tensor, k: int, nprobe: int = 1, flags: int = 0, pad_value: float = FLT_MAX
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        nq = q.shape[0]
+        with torch.cuda.device(self.dev):
+            if self.metric == "cosine":
+                q = normalized_rows(q)
+            q = q.contiguous()
+            probes = None
+            nprobe = 1
+            if self.quantizer is not None:
+                nprobe = max(1, min(int(nprobe), self.nlist))
+                if nprobe > MAX_FLAT_K:
+                    raise RuntimeError(f"nprobe={nprobe} is not supported: the coarse quantiser selects at most {MAX_FLAT_K} lists per query")
+                _, probes = self.quantizer.search(q, nprobe)
+            out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
+            out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
+            check(self.lib.vdb_ivf_pq_scan_topk(metric_code(self.metric), ptr(self.lists), ptr(self.list_ids), ptr(self.blk_off),
+                                                self.nlist, self.d, self.m, ptr(self.centroids), ptr(self.codebooks), ptr(probes), nprobe,
+                                                ptr(q), q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
+                                                _stream(self.dev)), "vdb_ivf_pq_scan_topk")
+        return out_d, out_i
+
+
 class HammingShard:
     """Sign-projection codes of one GPU's rows + the Hamming top-k scan (``faiss.IndexLSH``).
 

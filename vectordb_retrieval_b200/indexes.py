@@ -213,6 +213,78 @@ class GpuIndexIVFSQ8(GpuIndexIVFFlat):
         raise NotImplementedError("GpuIndexIVFSQ8 does not support index persistence")
 
 
+class GpuIndexIVFPQ(GpuIndexIVFFlat):
+    """``faiss.index_factory(d, "IVF<nlist>,PQ<m>", metric)``: IVF coarse quantiser + product-quantised residuals
+    (FAISS ``IndexIVFPQ``, 8 bits per sub-quantiser, by_residual); distances are those of the reconstructed vectors,
+    FAISS value conventions.  Persistence is not implemented."""
+
+    def __init__(self, d: int, nlist: int, m: int, metric="l2", **kwargs):
+        super().__init__(d, nlist, metric, **kwargs)
+        if m <= 0 or d % m != 0:
+            raise ValueError(f"PQ{m}: the dimension {d} must be a multiple of the number of sub-quantisers")
+        self.m = int(m)
+
+    def add(self, x) -> None:
+        if not self.is_trained:
+            raise RuntimeError("GpuIndexIVFPQ.add before train")
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexIVFPQ.add may be called once")
+        self._impl = engine.IVFPQShard(x, self.centroids, self.m, self._engine_metric(), self.device, seed=self.seed)
+        self.ntotal = int(x.shape[0])
+
+    def save(self, artifact_dir: str, context=None):
+        raise NotImplementedError("GpuIndexIVFPQ does not support index persistence")
+
+    def load(self, artifact_dir: str, context=None):
+        raise NotImplementedError("GpuIndexIVFPQ does not support index persistence")
+
+
+class GpuIndexPQ:
+    """``faiss.index_factory(d, "PQ<m>", metric)``: product quantiser over the rows themselves (FAISS ``IndexPQ``): one
+    code list, asymmetric distance computation against every row."""
+
+    def __init__(self, d: int, m: int, metric="l2", device=None, seed: int = 1234, normalize: bool = False):
+        if m <= 0 or d % m != 0:
+            raise ValueError(f"PQ{m}: the dimension {d} must be a multiple of the number of sub-quantisers")
+        self.d, self.m = int(d), int(m)
+        self.metric = _metric_name(metric)
+        self.normalize = bool(normalize)
+        self.device, self.seed = device, int(seed)
+        self.is_trained = True          # codebooks are trained inside add (train + add see the same rows in the reference)
+        self.ntotal = 0
+        self._impl: Optional[engine.IVFPQShard] = None
+
+    def train(self, x) -> None:
+        return None
+
+    def add(self, x) -> None:
+        if self._impl is not None:
+            raise RuntimeError("GpuIndexPQ.add may be called once")
+        metric = "cosine" if self.normalize and self.metric == "ip" else self.metric
+        self._impl = engine.IVFPQShard(x, None, self.m, metric, self.device, seed=self.seed)
+        self.ntotal = int(x.shape[0])
+
+    @property
+    def home(self) -> torch.device:
+        return self._impl.dev
+
+    def memory_bytes(self) -> int:
+        return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+        return self._impl.search(q, k, 1, 0, pad)
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        with torch.cuda.device(self.home):
+            q = engine.queries_to_device(queries, self.home, self.d)
+            return engine.results_to_host(*self.search_device(q, int(k)))
+
+
 class GpuIndexLSH:
     """``faiss.IndexLSH(d, nbits)``: sign bits of a random projection, Hamming top-k.
 
@@ -283,11 +355,14 @@ class GpuIndexLSH:
 
 _IVF_FLAT = re.compile(r"^IVF(\d+),Flat$")
 _IVF_SQ8 = re.compile(r"^IVF(\d+),SQ8$")
+_IVF_PQ = re.compile(r"^IVF(\d+),PQ(\d+)$")
+_PQ = re.compile(r"^PQ(\d+)$")
 
 
 def index_factory(d: int, key: str, metric="l2", **kwargs):
     """The subset of ``faiss.index_factory`` grammar that reaches the scan + top-k path:
-    ``"Flat"``, ``"IVF<nlist>,Flat"``, ``"IVF<nlist>,SQ8"`` and ``"LSH"``.  Anything else (PQ, HNSW, ...) is outside
+    ``"Flat"``, ``"IVF<nlist>,Flat"``, ``"IVF<nlist>,SQ8"``, ``"IVF<nlist>,PQ<m>"``, ``"PQ<m>"`` and ``"LSH"``.  Anything else
+    (HNSW, OPQ, other code widths, ...) is outside
     this build (out of scope) and raises ValueError at construction time."""
     key = key.strip()
     if key == "Flat":
@@ -298,6 +373,14 @@ def index_factory(d: int, key: str, metric="l2", **kwargs):
     m = _IVF_SQ8.match(key)
     if m:
         return GpuIndexIVFSQ8(d, int(m.group(1)), metric, **kwargs)
+    m = _IVF_PQ.match(key)
+    if m:
+        return GpuIndexIVFPQ(d, int(m.group(1)), int(m.group(2)), metric, **kwargs)
+    m = _PQ.match(key)
+    if m:
+        kwargs = {k_: v for k_, v in kwargs.items() if k_ in ("device", "seed", "normalize")}
+        return GpuIndexPQ(d, int(m.group(1)), metric, **kwargs)
     if key == "LSH":
         return GpuIndexLSH(d, kwargs.pop("nbits", 256), **kwargs)
-    raise ValueError(f"index key '{key}' is not supported by the CUDA build (supported: 'Flat', 'IVF<n>,Flat', 'IVF<n>,SQ8', 'LSH')")
+    raise ValueError(f"index key '{key}' is not supported by the CUDA build "
+                     "(supported: 'Flat', 'IVF<n>,Flat', 'IVF<n>,SQ8', 'IVF<n>,PQ<m>', 'PQ<m>', 'LSH')")
