@@ -649,8 +649,9 @@ class IVFPQShard:
                 q = normalized_rows(q)
             q = q.contiguous()
             probes = None
-            nprobe = 1
-            if self.quantizer is not None:
+            if self.quantizer is None:
+                nprobe = 1                                   # IndexPQ: the single list
+            else:
                 nprobe = max(1, min(int(nprobe), self.nlist))
                 if nprobe > MAX_FLAT_K:
                     raise RuntimeError(f"nprobe={nprobe} is not supported: the coarse quantiser selects at most {MAX_FLAT_K} lists per query")
