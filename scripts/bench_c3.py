@@ -102,6 +102,25 @@ def main() -> int:
                           "approx_code_gb": rows * shard.d16 * 16 / 1e9, "approx_code_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}), flush=True)
     del sq, shard
 
+    # IVF<nlist>,PQ<m> and PQ<m>: m = d one-byte sub-quantisers (the reference's glove50 rows use PQ50), look-up-table scan
+    for key in (f"IVF{args.nlist},PQ{d}", f"PQ{d}"):
+        t0 = time.time()
+        pq = indexes.index_factory(d, key, "ip", device=dev, normalize=True)
+        pq.train(base)
+        pq.add(base)
+        torch.cuda.synchronize()
+        print(json.dumps({"algo": "pq_build", "index_key": key, "train_plus_add_s": time.time() - t0,
+                          "list_bytes_per_row": int(pq._impl.m16 * 16)}), flush=True)
+        for nprobe in ((8, 32, 128) if key.startswith("IVF") else (1,)):
+            if hasattr(pq, "nprobe"):
+                pq.nprobe = nprobe
+            ms_total, (D, I) = timed(lambda: pq.search_device(q_dev.clone(), k), reps=3)
+            rows = (nprobe * args.n / args.nlist if key.startswith("IVF") else args.n) * args.nq
+            print(json.dumps({"algo": "pq", "index_key": key, "nprobe": nprobe, "recall@100": recall_at_k(gt, I.cpu().numpy(), 100),
+                              "ms_total": ms_total, "qps": args.nq / ms_total * 1e3, "table_lookups_per_s": rows * d / (ms_total * 1e-3)}),
+                  flush=True)
+        del pq
+
     lsh = indexes.GpuIndexLSH(d, 256, device=dev)
     lsh.add(base)
     rr = engine.Reranker(base, "cosine", dev)
