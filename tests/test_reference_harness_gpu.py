@@ -86,7 +86,7 @@ def test_reference_run_full_benchmark_cli_published_random_run(tmp_path):
     runs = sorted(os.listdir(out))
     assert len(runs) == 1 and runs[0].startswith("benchmark_")
     res = json.load(open(os.path.join(out, runs[0], "all_results.json")))["random"]
-    assert set(res) == {"exact", "exact_faiss_flat", "ivf_flat", "faiss_lsh", "lsh"}
+    assert set(res) == {"exact", "exact_faiss_flat", "ivf_flat", "ivf_sq8", "ivf_pq", "pq", "faiss_lsh", "lsh"}
     for name in ("exact", "exact_faiss_flat"):
         assert res[name]["recall@1"] == 1.0 and res[name]["recall@10"] == 1.0, (name, res[name])
         assert res[name]["n_train"] == 20000 and res[name]["n_test"] == 256 and res[name]["topk"] == 20
@@ -96,6 +96,10 @@ def test_reference_run_full_benchmark_cli_published_random_run(tmp_path):
     # published 0.4105 / 0.9672 are a neighbourhood, not a pin
     assert 0.30 < res["ivf_flat"]["recall@10"] < 0.55, res["ivf_flat"]["recall@10"]
     assert res["faiss_lsh"]["recall@10"] > 0.88, res["faiss_lsh"]["recall@10"]      # published with FAISS's own rotation: 0.967; here 0.922
+    # quantised indexes (published with FAISS's own k-means: ivf_sq8 0.509, ivf_pq 0.509, pq 0.967): neighbourhoods again
+    assert 0.40 < res["ivf_sq8"]["recall@10"] < 0.65, res["ivf_sq8"]["recall@10"]
+    assert 0.40 < res["ivf_pq"]["recall@10"] < 0.65, res["ivf_pq"]["recall@10"]
+    assert res["pq"]["recall@10"] > 0.90, res["pq"]["recall@10"]
     # the exact row's parameters name OUR classes through the reference's describe() plumbing
     assert res["exact"]["parameters"]["searcher"]["type"] == "LinearSearcher"
     assert res["exact"]["qps"] > 0 and res["exact"]["index_memory_mb"] > 0
