@@ -26,6 +26,8 @@
  *   - return value: 0 = ok, non-zero = error; text via vdb_last_error() (thread-local)
  *   - no C++ exception crosses this boundary
  *   - distances out: float32; ids out: int64 (row index + id_offset), -1 = padding
+ *   - tuning overrides read from the environment at call time (launch shape only, never results):
+ *     VDB_IVF_WPQ / VDB_RERANK_WPQ = 1 | 2 | 4 | 8 warps per query for the IVF list scan / the rerank kernel
  */
 #ifndef VDB_CUDA_H_
 #define VDB_CUDA_H_
