@@ -271,17 +271,23 @@ int vdb_ivf_sq8_scan_topk(int metric, const uint8_t* list_codes, const int32_t* 
  * configs/benchmark_config.yaml:36-50,61-72): IndexIVFPQ (by_residual) / IndexPQ.  codebooks [m][256][d/m] fp32 come
  * from the IVF k-means recipe run per sub-space by the host side.
  *   vdb_pq_encode         codes[i, s] = nearest of the 256 centroids of sub-quantiser s to x[i, s*dsub : (s+1)*dsub]
- *   vdb_bytes_fill        scatter byte rows [n, m] into interleaved-32 byte lists (layout of vdb_sq8_fill with d := m)
- *   vdb_ivf_pq_scan_topk  per probed list a table T[s][j] = |(q - c)_s - cb[s][j]|^2 (inner product: q_s . cb[s][j], plus
- *                         q . c per list) in shared memory, a row scores sum_s T[s][code_s]; centroids == NULL = zero
- *                         centroid, probes == NULL = the single list 0 (IndexPQ); conventions as vdb_ivf_scan_topk */
+ *   vdb_pq_bias           bias[i] = |r^_i|^2 + 2 c_i . r^_i of the row's decoded residual and its list centroid (NULL = zero)
+ *   vdb_bytes_fill        scatter byte rows [n, m] - and optionally one float per row - into interleaved-32 byte lists
+ *                         (layout of vdb_sq8_fill with d := m; list_values [n_blocks * 32] float)
+ *   vdb_ivf_pq_scan_topk  one table per query, T[s][j] = -2 q_s . cb[s][j] (inner product: q_s . cb[s][j]), in shared memory;
+ *                         L2: |q - c|^2 + bias_row + sum_s T[s][code_s] (clamped at 0), inner product: q . c + sum_s T[s][code_s];
+ *                         centroids == NULL = zero centroid, probes == NULL = the single list 0 (IndexPQ); list_bias may be
+ *                         NULL for inner product; conventions as vdb_ivf_scan_topk */
 int vdb_pq_encode(const float* x, int64_t n, int d, int64_t ld, const float* codebooks, int m, uint8_t* codes, void* stream);
+int vdb_pq_bias(const uint8_t* codes, int64_t n, int d, int m, const float* codebooks, const float* centroids,
+                const int32_t* assign, float* bias, void* stream);
 int vdb_bytes_fill(const uint8_t* rows, int64_t n, int m, const int32_t* assign, const int32_t* blk_off, int nlist,
-                   int32_t* cursor, uint8_t* lists, int32_t* list_ids, void* stream);
-int vdb_ivf_pq_scan_topk(int metric, const uint8_t* lists, const int32_t* list_ids, const int32_t* blk_off, int nlist,
-                         int d, int m, const float* centroids, const float* codebooks, const int64_t* probes, int nprobe,
-                         const float* q, int64_t ld_q, int64_t nq, int k, int flags, float pad_value, int64_t id_offset,
-                         float* out_d, int64_t* out_i, void* stream);
+                   int32_t* cursor, uint8_t* lists, int32_t* list_ids, const float* row_values, float* list_values,
+                   void* stream);
+int vdb_ivf_pq_scan_topk(int metric, const uint8_t* lists, const int32_t* list_ids, const float* list_bias,
+                         const int32_t* blk_off, int nlist, int d, int m, const float* centroids, const float* codebooks,
+                         const int64_t* probes, int nprobe, const float* q, int64_t ld_q, int64_t nq, int k, int flags,
+                         float pad_value, int64_t id_offset, float* out_d, int64_t* out_i, void* stream);
 
 /* ---- Hamming top-k on the tensor pipe (large bases, nbits <= 256) ----------------------------- */
 /* Same contract as vdb_hamming_topk ((distance, id) order, out_d / out_i [nq,k] pre-filled by the

@@ -632,14 +632,23 @@ class IVFPQShard:
             self.lists = torch.zeros(max(n_blocks, 1) * self.m16 * 32 * 16, dtype=torch.uint8, device=self.dev)
             self.list_ids = torch.full((max(n_blocks, 1) * 32,), -1, dtype=torch.int32, device=self.dev)
             cursor = torch.zeros(self.nlist, dtype=torch.int32, device=self.dev)
+            # per-row bias |r^|^2 + 2 c.r^ (L2): with it the scan needs one look-up table per query, not one per probed list
+            self.list_bias = None
+            row_bias = None
+            if metric == "l2":
+                row_bias = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+                check(self.lib.vdb_pq_bias(ptr(codes), self.n, self.d, self.m, ptr(self.codebooks), ptr(self.centroids), ptr(assign),
+                                           ptr(row_bias), s), "vdb_pq_bias")
+                self.list_bias = torch.zeros(max(n_blocks, 1) * 32, dtype=torch.float32, device=self.dev)
             check(self.lib.vdb_bytes_fill(ptr(codes), self.n, self.m, ptr(assign), ptr(blk_off), self.nlist, ptr(cursor),
-                                          ptr(self.lists), ptr(self.list_ids), s), "vdb_bytes_fill")
+                                          ptr(self.lists), ptr(self.list_ids), ptr(row_bias), ptr(self.list_bias), s), "vdb_bytes_fill")
             self.blk_off, self.counts = blk_off, counts
             torch.cuda.current_stream(self.dev).synchronize()
 
     def memory_bytes(self) -> int:
         q = self.quantizer.memory_bytes() if self.quantizer is not None else 0
-        return self.lists.numel() + self.list_ids.numel() * 4 + self.codes.numel() + self.codebooks.numel() * 4 + q
+        bias = self.list_bias.numel() * 4 if self.list_bias is not None else 0
+        return self.lists.numel() + self.list_ids.numel() * 4 + bias + self.codes.numel() + self.codebooks.numel() * 4 + q
 
     def search(self, q: torch.Tensor, k: int, nprobe: int = 1, flags: int = 0, pad_value: float = FLT_MAX
                ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -658,8 +667,8 @@ class IVFPQShard:
                 _, probes = self.quantizer.search(q, nprobe)
             out_d = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
             out_i = torch.empty((nq, k), dtype=torch.int64, device=self.dev)
-            check(self.lib.vdb_ivf_pq_scan_topk(metric_code(self.metric), ptr(self.lists), ptr(self.list_ids), ptr(self.blk_off),
-                                                self.nlist, self.d, self.m, ptr(self.centroids), ptr(self.codebooks), ptr(probes), nprobe,
+            check(self.lib.vdb_ivf_pq_scan_topk(metric_code(self.metric), ptr(self.lists), ptr(self.list_ids), ptr(self.list_bias),
+                                                ptr(self.blk_off), self.nlist, self.d, self.m, ptr(self.centroids), ptr(self.codebooks), ptr(probes), nprobe,
                                                 ptr(q), q.stride(0), nq, k, flags, pad_value, self.id_offset, ptr(out_d), ptr(out_i),
                                                 _stream(self.dev)), "vdb_ivf_pq_scan_topk")
         return out_d, out_i
