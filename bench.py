@@ -151,9 +151,14 @@ def _reference_numpy(base, queries):
         return None
     try:
         from vectordb_retrieval_b200 import plugin
+        try:                                              # torchrun exports OMP_NUM_THREADS=1: give NumPy's BLAS the box back
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=_host_cores(), user_api="blas")
+        except Exception:      # noqa: BLE001
+            pass
         mods = plugin.import_reference(ref_root)          # import stubs for faiss / matplotlib; NO plugin.install()
         out = {"kind": "reference-numpy", "unit": "queries/s", "cores": _host_cores(),
-               "impl": "src.algorithms.modular.LinearSearcher (unmodified, baseline/_ref), BLAS threads = numpy default"}
+               "impl": "src.algorithms.modular.LinearSearcher (unmodified, baseline/_ref), BLAS on all host cores"}
         for metric, nq, key in (("ip", 128, "ip"), ("l2", 2, "l2")):
             algo = mods["algorithms"].get_algorithm_instance(
                 "Composite", DIM, name=f"ref_{metric}", metric=metric, indexer={"type": "BruteForceIndexer"},
