@@ -266,7 +266,7 @@ class ShardedTopK:
         ex = self.buffers(nq, k)
         self.local_search(queries, k, (ex.d_loc[:nq], ex.i_loc[:nq]))
         if ex.world == 1:
-            return ex.d_loc[:nq], ex.i_loc[:nq]
+            return ex.d_loc[:nq].clone(), ex.i_loc[:nq].clone()      # the buffers are reused by the next call
         if self.exchange == "allgather":
             return ex.allgather_merge(self.merge)
         ex.alltoall_merge_slice(self.merge)
