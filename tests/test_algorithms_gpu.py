@@ -395,7 +395,7 @@ def test_smoke_config_c1_through_cli_entry(A, tmp_path):
     assert results["exact"]["n_train"] == 10000 and results["exact"]["n_test"] == 100
 
 
-@pytest.mark.parametrize("kind", ["exact", "ivf"])
+@pytest.mark.parametrize("kind", ["exact", "ivf", "ivf_sq8", "ivf_pq", "ivf_pq_ip", "pq"])
 def test_save_load_index_round_trip_is_bit_identical(A, kind, tmp_path):
     """save_index / load_index (reference base_algorithm.py:98-120; driver experiment_runner.py:308-344):
     a reloaded index answers exactly as the one that was saved."""
@@ -403,7 +403,11 @@ def test_save_load_index_round_trip_is_bit_identical(A, kind, tmp_path):
     x = rng.standard_normal((3000, 24)).astype(np.float32)
     q = rng.standard_normal((37, 24)).astype(np.float32)
     make = {"exact": lambda: A.ExactSearch("e", 24, metric="l2"),
-            "ivf": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,Flat", metric="l2", nprobe=4)}[kind]
+            "ivf": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,Flat", metric="l2", nprobe=4),
+            "ivf_sq8": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,SQ8", metric="l2", nprobe=4),
+            "ivf_pq": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,PQ4", metric="l2", nprobe=4),
+            "ivf_pq_ip": lambda: A.ApproximateSearch("a", 24, index_type="IVF16,PQ4", metric="ip", nprobe=4),
+            "pq": lambda: A.ApproximateSearch("a", 24, index_type="PQ6", metric="l2")}[kind]
     a = make()
     with pytest.raises(RuntimeError):
         a.save_index(str(tmp_path / "x"))

@@ -524,6 +524,31 @@ class IVFSQ8Shard:
     def memory_bytes(self) -> int:
         return self.list_codes.numel() + self.list_ids.numel() * 4 + self.quantizer.memory_bytes() + 8 * self.d
 
+    def state(self) -> Dict[str, np.ndarray]:
+        return {"centroids": self.centroids.cpu().numpy(), "list_codes": self.list_codes.cpu().numpy(),
+                "list_ids": self.list_ids.cpu().numpy(), "blk_off": self.blk_off.cpu().numpy(),
+                "counts": self.counts.cpu().numpy(), "assign": self.assign.cpu().numpy(),
+                "vmin": self.vmin.cpu().numpy(), "vdiff": self.vdiff.cpu().numpy(),
+                "meta": np.array([self.n, self.d, self.id_offset, self.nlist, self.n_blocks], dtype=np.int64)}
+
+    @classmethod
+    def from_state(cls, state: Dict[str, np.ndarray], metric: str, device=None) -> "IVFSQ8Shard":
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.n, self.d, self.id_offset, self.nlist, self.n_blocks = (int(v) for v in state["meta"])
+        self.d16 = self.lib.vdb_sq8_d16(self.d)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)    # noqa: E731
+        self.centroids = to(state["centroids"])
+        self.list_codes, self.list_ids, self.blk_off = to(state["list_codes"]), to(state["list_ids"]), to(state["blk_off"])
+        self.counts, self.assign = to(state["counts"]), to(state["assign"])
+        self.vmin, self.vdiff = to(state["vmin"]), to(state["vdiff"])
+        if self.list_codes.numel() != max(self.n_blocks, 1) * self.d16 * 32 * 16 or self.list_ids.numel() != max(self.n_blocks, 1) * 32:
+            raise RuntimeError("persisted IVF-SQ8 lists do not match their block count")
+        self.quantizer = FlatShard(self.centroids, "l2" if metric == "l2" else "ip", self.dev)
+        return self
+
     def codes_by_row(self) -> np.ndarray:
         """[n, d] uint8 codes in row order (test hook: undoes the interleaved list layout on the host)."""
         ids = self.list_ids.cpu().numpy()
@@ -644,6 +669,38 @@ class IVFPQShard:
                                           ptr(self.lists), ptr(self.list_ids), ptr(row_bias), ptr(self.list_bias), s), "vdb_bytes_fill")
             self.blk_off, self.counts = blk_off, counts
             torch.cuda.current_stream(self.dev).synchronize()
+
+    def state(self) -> Dict[str, np.ndarray]:
+        out = {"codebooks": self.codebooks.cpu().numpy(), "codes": self.codes.cpu().numpy(), "lists": self.lists.cpu().numpy(),
+               "list_ids": self.list_ids.cpu().numpy(), "blk_off": self.blk_off.cpu().numpy(), "counts": self.counts.cpu().numpy(),
+               "assign": self.assign.cpu().numpy(),
+               "meta": np.array([self.n, self.d, self.id_offset, self.nlist, self.m], dtype=np.int64)}
+        if self.centroids is not None:
+            out["centroids"] = self.centroids.cpu().numpy()
+        if self.list_bias is not None:
+            out["list_bias"] = self.list_bias.cpu().numpy()
+        return out
+
+    @classmethod
+    def from_state(cls, state: Dict[str, np.ndarray], metric: str, device=None) -> "IVFPQShard":
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.dev = _require_cuda(device)
+        self.metric = metric
+        self.n, self.d, self.id_offset, self.nlist, self.m = (int(v) for v in state["meta"])
+        self.m16 = self.lib.vdb_sq8_d16(self.m)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)    # noqa: E731
+        self.codebooks, self.codes = to(state["codebooks"]), to(state["codes"])
+        self.lists, self.list_ids, self.blk_off = to(state["lists"]), to(state["list_ids"]), to(state["blk_off"])
+        self.counts, self.assign = to(state["counts"]), to(state["assign"])
+        self.centroids = to(state["centroids"]) if "centroids" in state else None
+        self.list_bias = to(state["list_bias"]) if "list_bias" in state else None
+        if tuple(self.codebooks.shape) != (self.m, 256, self.d // self.m) or self.lists.numel() != self.list_ids.numel() * self.m16 * 16:
+            raise RuntimeError("persisted PQ codebooks / lists do not match their header")
+        if (metric == "l2") != (self.list_bias is not None):
+            raise RuntimeError(f"persisted PQ index was not built for metric '{metric}'")
+        self.quantizer = None if self.centroids is None else FlatShard(self.centroids, "l2" if metric == "l2" else "ip", self.dev)
+        return self
 
     def memory_bytes(self) -> int:
         q = self.quantizer.memory_bytes() if self.quantizer is not None else 0

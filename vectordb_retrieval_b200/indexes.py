@@ -196,7 +196,8 @@ class GpuIndexIVFFlat:
 class GpuIndexIVFSQ8(GpuIndexIVFFlat):
     """``faiss.index_factory(d, "IVF<nlist>,SQ8", metric)``: the IVF-Flat coarse quantiser with inverted lists of 8-bit
     scalar-quantised residuals (FAISS ``IndexIVFScalarQuantizer``, QT_8bit, by_residual; value conventions of FAISS:
-    squared L2 ascending / inner product descending, of the DECODED vectors).  Persistence is not implemented."""
+    squared L2 ascending / inner product descending, of the DECODED vectors).  save / load keep the code lists, the
+    quantiser's ranges and the centroids bit for bit."""
 
     def add(self, x) -> None:
         if not self.is_trained:
@@ -206,17 +207,35 @@ class GpuIndexIVFSQ8(GpuIndexIVFFlat):
         self._impl = engine.IVFSQ8Shard(x, self.centroids, self._engine_metric(), self.device)
         self.ntotal = int(x.shape[0])
 
+    _KIND, _SHARD = "ivf_sq8", engine.IVFSQ8Shard
+
     def save(self, artifact_dir: str, context=None):
-        raise NotImplementedError("GpuIndexIVFSQ8 does not support index persistence")
+        from . import persist
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        return persist.write_artifact(artifact_dir, self._KIND, self._impl.state(), self._meta(), context)
+
+    def _meta(self):
+        return {"d": self.d, "nlist": self.nlist, "metric": self.metric, "normalize": self.normalize,
+                "nprobe": int(self.nprobe), "ntotal": self.ntotal}
 
     def load(self, artifact_dir: str, context=None):
-        raise NotImplementedError("GpuIndexIVFSQ8 does not support index persistence")
+        from . import persist
+        arrays, manifest = persist.read_artifact(artifact_dir, self._KIND, context)
+        meta, mine = manifest["meta"], self._meta()
+        for key in mine:
+            if key not in ("nprobe", "ntotal", "normalize") and meta.get(key) != mine[key]:
+                raise RuntimeError(f"persisted {self._KIND} index {meta} does not match this index ({key}={mine[key]})")
+        self._impl = self._SHARD.from_state(arrays, self._engine_metric(), self.device)
+        self.centroids = arrays["centroids"]
+        self.is_trained, self.ntotal = True, int(meta["ntotal"])
+        return manifest
 
 
 class GpuIndexIVFPQ(GpuIndexIVFFlat):
     """``faiss.index_factory(d, "IVF<nlist>,PQ<m>", metric)``: IVF coarse quantiser + product-quantised residuals
     (FAISS ``IndexIVFPQ``, 8 bits per sub-quantiser, by_residual); distances are those of the reconstructed vectors,
-    FAISS value conventions.  Persistence is not implemented."""
+    FAISS value conventions.  save / load keep codebooks, code lists, biases and centroids bit for bit."""
 
     def __init__(self, d: int, nlist: int, m: int, metric="l2", **kwargs):
         super().__init__(d, nlist, metric, **kwargs)
@@ -232,11 +251,13 @@ class GpuIndexIVFPQ(GpuIndexIVFFlat):
         self._impl = engine.IVFPQShard(x, self.centroids, self.m, self._engine_metric(), self.device, seed=self.seed)
         self.ntotal = int(x.shape[0])
 
-    def save(self, artifact_dir: str, context=None):
-        raise NotImplementedError("GpuIndexIVFPQ does not support index persistence")
+    _KIND, _SHARD = "ivf_pq", engine.IVFPQShard
 
-    def load(self, artifact_dir: str, context=None):
-        raise NotImplementedError("GpuIndexIVFPQ does not support index persistence")
+    def _meta(self):
+        return dict(GpuIndexIVFSQ8._meta(self), m=self.m)
+
+    save = GpuIndexIVFSQ8.save
+    load = GpuIndexIVFSQ8.load
 
 
 class GpuIndexPQ:
@@ -270,6 +291,24 @@ class GpuIndexPQ:
 
     def memory_bytes(self) -> int:
         return 0 if self._impl is None else self._impl.memory_bytes()
+
+    def save(self, artifact_dir: str, context=None):
+        from . import persist
+        if self._impl is None:
+            raise RuntimeError("index is empty")
+        meta = {"d": self.d, "m": self.m, "metric": self.metric, "normalize": self.normalize, "ntotal": self.ntotal}
+        return persist.write_artifact(artifact_dir, "pq", self._impl.state(), meta, context)
+
+    def load(self, artifact_dir: str, context=None):
+        from . import persist
+        arrays, manifest = persist.read_artifact(artifact_dir, "pq", context)
+        meta = manifest["meta"]
+        if int(meta["d"]) != self.d or int(meta["m"]) != self.m or meta["metric"] != self.metric:
+            raise RuntimeError(f"persisted PQ index {meta} does not match d={self.d} m={self.m} metric={self.metric}")
+        metric = "cosine" if self.normalize and self.metric == "ip" else self.metric
+        self._impl = engine.IVFPQShard.from_state(arrays, metric, self.device)
+        self.ntotal = int(meta["ntotal"])
+        return manifest
 
     def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._impl is None:
