@@ -136,7 +136,7 @@ int vdb_debug_read_prof(uint64_t* out8);
 int vdb_flat_set_seeding(int sample_tiles, int rank);
 /* The sample is capped so that the guess's expected rank in the shard, rank * N / S rows, stays >= margin * k'
  * (k' = kept candidates, 128 for k = 100): a smaller margin allows a larger sample and a tighter guess on small
- * shards at a higher (still verified and repaired) chance of a redo.  0 = default max(4, 64 / rank). */
+ * shards at a higher (still verified and repaired) chance of a redo.  0 = default max(3, 48 / rank). */
 int vdb_flat_set_seeding_margin(int margin);
 /* Number of queries re-scanned since the last call (reads and clears a device counter). */
 int vdb_debug_redo_queries(uint64_t* out);

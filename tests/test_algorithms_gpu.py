@@ -307,7 +307,7 @@ def test_ivf_pipeline_given_same_centroids_and_recall(A, metric):
     d2, i2 = legacy.batch_search(queries, 10)
     _check(oracle.faiss_flat_search(base, queries, 10, "l2"), (d2, i2))     # nprobe == nlist is exact
     with pytest.raises(ValueError):
-        A.get_algorithm_instance("ApproximateSearch", 24, name="pq", index_type="IVF64,PQ8", metric="l2")
+        A.get_algorithm_instance("ApproximateSearch", 24, name="hnsw", index_type="IVF64,HNSW32", metric="l2")
 
 
 def test_ivf_sq8_through_the_factory_indexer(A):

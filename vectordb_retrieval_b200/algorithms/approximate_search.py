@@ -1,8 +1,9 @@
-"""``ApproximateSearch`` on the CUDA IVF-Flat path (reference: src/algorithms/approximate_search.py:6-87).
+"""``ApproximateSearch`` on the CUDA scan paths (reference: src/algorithms/approximate_search.py:6-87).
 
 The reference hands ``index_type`` to ``faiss.index_factory``; this build accepts the part of
-that grammar which is a scan + top-k - ``"Flat"`` and ``"IVF<nlist>,Flat"`` - and rejects the rest
-with ValueError at construction (PQ/SQ/HNSW are out of scope).  Values follow
+that grammar which is a scan + top-k - ``"Flat"``, ``"IVF<nlist>,Flat"``, ``"IVF<nlist>,SQ8"``,
+``"IVF<nlist>,PQ<m>"`` and ``"PQ<m>"`` - and rejects the rest with ValueError at construction (HNSW, OPQ and other
+code widths are out of scope).  Values follow
 raw FAISS: squared L2 ascending / inner product descending; only ``'l2'`` selects L2
 (approximate_search.py:25); ``nprobe`` comes from the constructor kwargs (approximate_search.py:50-51)."""
 from __future__ import annotations
@@ -17,10 +18,11 @@ from .base_algorithm import BaseAlgorithm
 class ApproximateSearch(BaseAlgorithm):
     def __init__(self, name: str, dimension: int, index_type: str, metric: str = "l2", **kwargs: Any) -> None:
         super().__init__(name, dimension, **kwargs)
-        from ..indexes import _IVF_FLAT
-        if index_type.strip() != "Flat" and not _IVF_FLAT.match(index_type.strip()):
+        from ..indexes import _IVF_FLAT, _IVF_PQ, _IVF_SQ8, _PQ
+        key = index_type.strip()
+        if key != "Flat" and not any(rx.match(key) for rx in (_IVF_FLAT, _IVF_SQ8, _IVF_PQ, _PQ)):
             raise ValueError(f"index_type '{index_type}' is not supported by the CUDA build "
-                             "(supported: 'Flat', 'IVF<nlist>,Flat')")
+                             "(supported: 'Flat', 'IVF<nlist>,Flat', 'IVF<nlist>,SQ8', 'IVF<nlist>,PQ<m>', 'PQ<m>')")
         self.index_type = index_type
         self.metric = "l2" if metric == "l2" else "ip"
         self.index = None

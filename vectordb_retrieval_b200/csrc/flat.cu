@@ -102,10 +102,11 @@ static thread_local int g_debug_mode = 0;
 // every query after the main pass, and a query with fewer than k' of them (tau was too tight) is
 // reset and re-scanned from an infinite bound by a third launch that skips every query tile
 // without such a query (normally all of them).  S is capped so that r * N / S >= margin * k':
-// for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) ~ 1e-10.
+// for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r): 1e-4 per query at r = 16, margin 3
+// (about one redone query tile per 10k-query search, 1/40 of a scan), 5e-6 at margin 4.
 static thread_local int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
 static thread_local int g_pre_rank = 16;      // r (1..32)
-static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(4, 64 / r)
+static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(3, 48 / r)
 __device__ unsigned long long g_redo_queries;
 
 struct PrePlan {
@@ -135,7 +136,7 @@ static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, in
   PrePlan pp{};
   if (main_plan.cta_group == 0 || g_pre_tiles <= 0) return pp;
   const int r = std::min(std::max(g_pre_rank, 1), kSeedKeep);
-  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(4, 64 / r);    // r = 16: 4 (was 8: 18 % slower on a 125k-row shard)
+  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(3, 48 / r);    // r = 16: 3 (125k-row shard: 8 -> 2.01 ms, 4 -> 1.60 ms, 3 -> 1.46 ms)
   const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
   const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
   if (s_tiles < 4) return pp;                       // small shard (< 64k rows at k' = 128): the sample would not pay for itself
