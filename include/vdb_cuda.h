@@ -131,12 +131,14 @@ int vdb_debug_read_prof(uint64_t* out8);
 /* Seeded bounds of the tcgen05 scan (see flat.cu): a pre-pass over `sample_tiles` strided base
  * tiles (256 rows each; 0 disables seeding) gives every query the `rank`-th smallest sampled key
  * as its starting bound; queries whose guess turns out too tight are detected after the main pass
- * and re-scanned from an infinite bound, so results never depend on these knobs.  Defaults 64, 16.
+ * and re-scanned from an infinite bound, so results never depend on these knobs.  Defaults 64, 0 (rank chosen per shard: 16, or 32 on
+ * small shards where the margin cap below binds; 1 <= rank <= 32 pins it).
  * Debug mode 6 forces every query through the re-scan (test hook), mode 7 disables seeding. */
 int vdb_flat_set_seeding(int sample_tiles, int rank);
 /* The sample is capped so that the guess's expected rank in the shard, rank * N / S rows, stays >= margin * k'
  * (k' = kept candidates, 128 for k = 100): a smaller margin allows a larger sample and a tighter guess on small
- * shards at a higher (still verified and repaired) chance of a redo.  0 = default max(3, 48 / rank). */
+ * shards at a higher (still verified and repaired) chance of a redo.  0 = default: 3 at rank 32, else max(4, 64 / rank) - one failed guess costs a whole wave of the redo launch, so the
+ * failure probability per query, P(Poisson(rank / margin) >= rank), has to stay far below 1 / nq. */
 int vdb_flat_set_seeding_margin(int margin);
 /* Number of queries re-scanned since the last call (reads and clears a device counter). */
 int vdb_debug_redo_queries(uint64_t* out);

@@ -21,8 +21,8 @@ def main():
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
     for rows, nq in ((125_000, 10_000), (250_000, 10_000), (500_000, 10_000), (1_000_000, 10_000), (1_000_000, 1_250)):
         shard = engine.FlatShard(base[:rows], "l2", dev)
-        for tiles, margin in ((64, 8), (64, 4), (128, 4), (128, 3), (256, 4)):
-            lib.vdb_flat_set_seeding(tiles, 16)
+        for tiles, rank, margin in ((64, 0, 0), (64, 16, 4), (64, 16, 3), (64, 32, 3), (64, 32, 4), (128, 32, 3)):
+            lib.vdb_flat_set_seeding(tiles, rank)
             lib.vdb_flat_set_seeding_margin(margin)
             for _ in range(3):
                 shard.search(q[:nq], 100)
@@ -41,10 +41,10 @@ def main():
             lib.vdb_flat_timing_enable(0)
             lib.vdb_debug_redo_queries(ctypes.byref(redo))
             scan = sorted(buf[i] for i in range(n.value))[n.value // 2]
-            print(json.dumps({"rows": rows, "nq": nq, "sample_tiles": tiles, "margin": margin, "search_ms": sorted(ts)[len(ts) // 2],
+            print(json.dumps({"rows": rows, "nq": nq, "sample_tiles": tiles, "rank": rank, "margin": margin, "search_ms": sorted(ts)[len(ts) // 2],
                               "main_scan_ms": scan, "redo_queries_in_8_searches": int(redo.value)}), flush=True)
         del shard
-    lib.vdb_flat_set_seeding(64, 16)
+    lib.vdb_flat_set_seeding(64, 0)
     lib.vdb_flat_set_seeding_margin(0)
 
 

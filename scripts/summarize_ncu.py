@@ -21,10 +21,10 @@ def short(name: str) -> str:
     name = name.replace("void ", "")
     if name.startswith("cutlass") or "gemm" in name.lower():
         return "cuBLAS TF32 GEMM 8192^3 (bench.py's live yardstick, outside the timed region)"
-    if "flat_scan_tc_kernel<" in name:     # the template arguments tell the seeding pre-pass (..., 32, 0, 1) from the main scan
+    if "flat_scan_tc_kernel<" in name:     # the template arguments tell the seeding pre-pass (..., 32, 0, 16) from the main scan
         args = name.split("flat_scan_tc_kernel<")[1].split(">")[0].replace("(int)", "").replace("(bool)", "").replace(" ", "")
         parts = args.split(",")
-        seed = len(parts) >= 5 and parts[4] == "1"
+        seed = len(parts) >= 5 and parts[4] != "0"      # kept minima per item (16 / 32; "1" in captures before round 2's last build)
         ham = parts[5] if len(parts) >= 6 else "0"
         kind = " (seeding pre-pass)" if seed else {"1": " (Hamming scan: bf16 codes, collect within the bound)"}.get(ham, " (main scan)")
         return "flat_scan_tc_kernel<" + args + ">" + kind

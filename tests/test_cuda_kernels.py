@@ -442,7 +442,9 @@ def test_seeded_bounds_misleading_sample_takes_the_redo_pass(eng):
     """Adversarial row order: the sampled tiles hold only rows close to the queries, so the guessed
     bound is far too tight for the rest of the base.  The verify kernel must catch those queries and
     the redo pass must still return the exact answer."""
-    n, d, nq, k = 262144, 32, 64, 100          # 1024 tiles; k' = 128 -> 16 sampled tiles, stride 64
+    n, d, nq, k = 262144, 32, 64, 100          # 1024 tiles; k' = 128, rank 16, margin 4 -> 32 sampled tiles, stride 32
+    lib = eng._lib.load()
+    assert lib.vdb_flat_set_seeding(64, 16) == 0 and lib.vdb_flat_set_seeding_margin(4) == 0   # the layout below is built for this sample
     rng = np.random.RandomState(3)
     q = rng.randn(nq, d).astype(np.float32)
     # (a) guesses far too loose: the sampled tiles hold only far rows -> slower, never wrong, no redo
@@ -468,6 +470,7 @@ def test_seeded_bounds_misleading_sample_takes_the_redo_pass(eng):
     redo = _redo_count()
     ref = oracle.faiss_flat_search(base2, q, k, "l2")
     _check(ref, (D.cpu().numpy(), I.cpu().numpy()))
+    assert lib.vdb_flat_set_seeding(64, 0) == 0 and lib.vdb_flat_set_seeding_margin(0) == 0
     assert redo > 0, "expected the misleading sample to force at least one query through the redo pass"
 
 

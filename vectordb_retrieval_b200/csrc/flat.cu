@@ -102,16 +102,24 @@ static thread_local int g_debug_mode = 0;
 // every query after the main pass, and a query with fewer than k' of them (tau was too tight) is
 // reset and re-scanned from an infinite bound by a third launch that skips every query tile
 // without such a query (normally all of them).  S is capped so that r * N / S >= margin * k':
-// for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r): 1e-4 per query at r = 16, margin 3
-// (about one redone query tile per 10k-query search, 1/40 of a scan), 5e-6 at margin 4.
+// for a random sample P(fewer than k' rows below tau) = P(Poisson(r / margin) >= r) per query - and ONE such
+// query costs a whole wave of the redo launch (its query tile's items run as long as any item of the main pass),
+// so the product with 10k queries has to stay far below 1:
+//     r = 16, margin 4: 5e-6      r = 16, margin 3: 1e-4 (a redo in most 10k-query searches: 2.4 ms instead of
+//     r = 32, margin 3: 7e-8                               1.46 ms on a 125k-row shard - measured, rejected)
+// The rank is chosen per shard (g_pre_rank = 0): 16 with margin 4 while the 64-tile sample is the binding limit
+// (large shards; the guess's expected rank is 16 N / 64 tiles), 32 with margin 3 where the margin cap binds and
+// that gives a clearly tighter guess (shards under ~200k rows: the sample grows from 3 % to 8 % of the rows, and
+// the main scan of a 125k-row shard drops from 1.33 to 1.18 ms).
 static thread_local int g_pre_tiles = 64;     // sample size in base tiles (vdb_flat_set_seeding)
-static thread_local int g_pre_rank = 16;      // r (1..32)
-static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default max(3, 48 / r)
+static thread_local int g_pre_rank = 0;       // r (1..kSeedKeep); 0 = per shard, see above
+static thread_local int g_pre_margin = 0;     // r * N / S >= margin * k'; 0 = default: 3 at r >= 32, else max(4, 64 / r)
 __device__ unsigned long long g_redo_queries;
 
 struct PrePlan {
   bool on;
   int stride;          // sampled tile t is base tile t * stride
+  int rank;            // tau = the rank-th smallest sampled chunk minimum
   FlatPlan plan;       // decomposition of the sample
 };
 
@@ -132,15 +140,24 @@ __global__ void flat_init_kernel(uint32_t* thr, int64_t nq_pad, int* pool_cnt, i
   if (i < n_active) active[i] = 0;
 }
 
+static int default_margin(int r) { return g_pre_margin > 0 ? g_pre_margin : (r >= 32 ? 3 : std::max(4, 64 / r)); }
+
 static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, int kpad, int sm, int kp) {
   PrePlan pp{};
   if (main_plan.cta_group == 0 || g_pre_tiles <= 0) return pp;
-  const int r = std::min(std::max(g_pre_rank, 1), kSeedKeep);
-  const int margin = g_pre_margin > 0 ? g_pre_margin : std::max(3, 48 / r);    // r = 16: 3 (125k-row shard: 8 -> 2.01 ms, 4 -> 1.60 ms, 3 -> 1.46 ms)
-  const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(margin) * kp);
-  const int s_tiles = static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
-  if (s_tiles < 4) return pp;                       // small shard (< 64k rows at k' = 128): the sample would not pay for itself
+  auto sample_for = [&](int r) {      // tiles: the configured sample, capped so that the guess keeps its margin
+    const int64_t cap = static_cast<int64_t>(r) * main_plan.n_tiles / (static_cast<int64_t>(default_margin(r)) * kp);
+    return static_cast<int>(std::min<int64_t>(g_pre_tiles, cap));
+  };
+  int r = std::min(g_pre_rank, kSeedKeep);
+  if (r <= 0) {                       // per shard: the guess's expected rank in the shard is r * n_tiles / S rows-per-tile units
+    const int s16 = sample_for(16), s32 = sample_for(32);
+    r = (s32 >= 4 && (s16 < 4 || 32.0 * s16 < 0.85 * 16.0 * s32)) ? 32 : 16;
+  }
+  const int s_tiles = sample_for(r);
+  if (s_tiles < 4) return pp;                       // small shard (< ~50k rows at k' = 128): the sample would not pay for itself
   pp.on = true;
+  pp.rank = r;
   pp.stride = main_plan.n_tiles / s_tiles;
   pp.plan = make_plan(impl, nq, static_cast<int64_t>(s_tiles) * main_plan.tile_rows, kpad, sm);
   return pp;
@@ -151,12 +168,12 @@ static PrePlan make_pre_plan(int impl, int64_t nq, const FlatPlan& main_plan, in
 // the scan compares with.  A chunk minimum is a real key, so tau's rank among the sampled rows is
 // at least `rank`: slightly looser than the exact order statistic, never tighter.
 __global__ void __launch_bounds__(128)
-flat_tau_kernel(const float* __restrict__ seed, int n_chunks, int64_t nq, int rank, int force_fail,
+flat_tau_kernel(const float* __restrict__ seed, int n_chunks, int keep, int64_t nq, int rank, int force_fail,
                 uint32_t* __restrict__ thr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + warp;
   if (q >= nq) return;
-  const int total = n_chunks * kSeedKeep;
+  const int total = n_chunks * keep;
   const float* v = seed + q * total;
   uint64_t best[1] = {kEmpty};
   for (int base = 0; base < total; base += 128) {            // four independent loads in flight per lane
@@ -553,7 +570,7 @@ static int make_operand_map_uncached(CUtensorMap* map, const float* ptr, int64_t
   return 0;
 }
 
-template <int CG, bool ARES, int KP, bool DENSE, bool SEED = false, int HAM = 0>
+template <int CG, bool ARES, int KP, bool DENSE, int SEED = 0, int HAM = 0>
 static int launch_tc(const CUtensorMap& mqh, const CUtensorMap& mql, const CUtensorMap& mbh, const CUtensorMap& mbl,
                      const FlatScanParams& P, int clusters, cudaStream_t stream) {
   auto kern = flat_scan_tc_kernel<CG, ARES, KP, DENSE, SEED, HAM>;
@@ -641,12 +658,19 @@ static int run_scan(int impl, const float* hi, const float* lo, int64_t n_pad, i
     return 3;
   const bool ares = P.kb <= tc::kMaxResidentKb;
   if constexpr (KP == 32) {   // the seeding pre-pass is instantiated once, under the smallest pool size
+    if (P.seed_out != nullptr && P.seed_keep > 16) {       // kept minima per item: 16 or 32 (the insertion network's depth)
+      if (plan.cta_group == 2)
+        return ares ? launch_tc<2, true, KP, false, 32>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                    : launch_tc<2, false, KP, false, 32>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+      return ares ? launch_tc<1, true, KP, false, 32>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                  : launch_tc<1, false, KP, false, 32>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+    }
     if (P.seed_out != nullptr) {
       if (plan.cta_group == 2)
-        return ares ? launch_tc<2, true, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
-                    : launch_tc<2, false, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
-      return ares ? launch_tc<1, true, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
-                  : launch_tc<1, false, KP, false, true>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+        return ares ? launch_tc<2, true, KP, false, 16>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                    : launch_tc<2, false, KP, false, 16>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
+      return ares ? launch_tc<1, true, KP, false, 16>(mqh, mql, mbh, mbl, P, plan.clusters, stream)
+                  : launch_tc<1, false, KP, false, 16>(mqh, mql, mbh, mbl, P, plan.clusters, stream);
     }
   }
   if constexpr (KP == 32) {   // the dense-key test hook exists for the smallest pool size only
@@ -744,11 +768,12 @@ static int flat_topk_impl(int metric, const float* hi, const float* lo, const fl
     Q.n_tiles = pre.plan.n_tiles; Q.tiles_per_chunk = pre.plan.tiles_per_chunk; Q.n_chunks = pre.plan.n_chunks;
     Q.n_pools = pre.plan.n_pools; Q.tile_stride = pre.stride;
     Q.seed_out = reinterpret_cast<float*>(w + off_seed);
+    Q.seed_keep = pre.rank > 16 ? 32 : 16;
     Q.dbg = 0;
     const int rc0 = run_scan<32>(impl, hi, lo, n_pad, kpad, q_hi, q_lo, nq_pad, pre.plan, Q, sm, stream);
     if (rc0) return rc0;
     flat_tau_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, 0, stream>>>(
-        Q.seed_out, Q.n_chunks, nq, std::min(std::max(g_pre_rank, 1), kSeedKeep), g_debug_mode == 6, P.thr);
+        Q.seed_out, Q.n_chunks, Q.seed_keep, nq, pre.rank, g_debug_mode == 6, P.thr);
     VDB_CHECK_CUDA(cudaGetLastError());
     launches += 2;
   }
@@ -930,7 +955,7 @@ int vdb_debug_read_prof(uint64_t* out8) {
 }
 
 int vdb_flat_set_seeding(int sample_tiles, int rank) {
-  VDB_REQUIRE(sample_tiles >= 0 && rank >= 1 && rank <= kSeedKeep, "vdb_flat_set_seeding: sample_tiles >= 0, 1 <= rank <= %d", kSeedKeep);
+  VDB_REQUIRE(sample_tiles >= 0 && rank >= 0 && rank <= kSeedKeep, "vdb_flat_set_seeding: sample_tiles >= 0, 0 (per shard) <= rank <= %d", kSeedKeep);
   g_pre_tiles = sample_tiles;
   g_pre_rank = rank;
   return 0;
@@ -1134,9 +1159,9 @@ static int hamming_topk_tc_impl(bool fp16, const void* base_bf16, const float* n
     return 3;
   if (fp16) {
     VDB_REQUIRE(nbits % 2 == 0, "vdb_hamming_topk_tc_f16: nbits must be even (the fp16 epilogue halves key + nbits exactly)");
-    if (launch_tc<2, true, 32, false, false, 2>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+    if (launch_tc<2, true, 32, false, 0, 2>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
   } else {
-    if (launch_tc<2, true, 32, false, false, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
+    if (launch_tc<2, true, 32, false, 0, 1>(mq, mq, mb, mb, P, plan.clusters, s)) return 3;
   }
   ham_select_kernel<<<static_cast<unsigned>((nq + 3) / 4), 128, static_cast<size_t>(4) * (bins + 1) * sizeof(int), s>>>(
       list, lcnt, segs, cap, nq, nbits, k, static_cast<int>(std::min<int64_t>(k, n)), static_cast<uint32_t>(n), id_offset, out_d,

@@ -59,7 +59,8 @@ struct FlatScanParams {
   int dense_only;       // kDense: write the keys and keep no candidates (the selection runs as a separate kernel)
   int tile_stride;      // base tile visited by step t is t * tile_stride (1 = every tile; > 1 = the strided sample of the pre-pass)
   const int* qtile_active;  // redo pass: only query tiles flagged here are processed (nullptr = all)
-  float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeedKeep] smallest chunk minima per (query, item)
+  float* seed_out;      // seeding pre-pass (kSeed): [nq_pad][n_chunks][kSeed] smallest chunk minima per (query, item)
+  int seed_keep;        // ... kSeed of the variant to launch (16 or 32); host side only
   // Hamming scan (kHam, flat.cu): operands are bf16 +-1 codes (queries negated, so key = -dot and
   // ham = (nbits + key) / 2); every key within the query's bound is appended to the (segment, query) list.
   // A chunk is cut into two segments: its first ceil(n/2) tiles are drained by epilogue group 0 (warps 4..7, TMEM
@@ -75,7 +76,7 @@ struct FlatScanParams {
 // bring-up counters (vdb_debug_read_prof): see include/vdb_cuda.h for the slots
 __device__ unsigned long long g_prof[8];
 
-constexpr int kSeedKeep = 16;   // chunk minima a query keeps per item of the seeding pre-pass
+constexpr int kSeedKeep = 32;   // most chunk minima a query keeps per item of the seeding pre-pass (kSeed = 16 or 32: the largest usable rank)
 
 namespace tc {
 constexpr int kThreads = 256;
@@ -99,10 +100,10 @@ constexpr int smem_bytes() {
 }  // namespace tc
 
 // kSeed: the seeding pre-pass (flat.cu).  Same pipeline, but the epilogue keeps no candidates: per
-// (query, item) it tracks the kSeedKeep smallest *minima of 32-row chunks* in registers (a branch-free
+// (query, item) it tracks the kSeed (16 or 32) smallest *minima of 32-row chunks* in registers (a branch-free
 // insertion network, so the pass runs at the contraction's speed) and writes them out at the end of
 // the item; the r-th smallest of them over the sample is the query's starting bound for the main pass.
-template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, bool kSeed = false, int kHam = 0>
+template <int kCtaGroup, bool kAResident, int KP, bool kDense = false, int kSeedN = 0, int kHam = 0>
 __global__ void __launch_bounds__(tc::threads<kHam>(), 1)
 flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -115,6 +116,8 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   constexpr int CAP = pool_cap(KP);
   constexpr uint32_t IDESC = make_idesc_tf32(UMMA_M, UMMA_N);
   constexpr uint32_t IDESC_BF16 = kHam == 2 ? make_idesc_f16_acc16(UMMA_M, UMMA_N) : make_idesc_bf16(UMMA_M, UMMA_N);
+  constexpr bool kSeed = kSeedN != 0;         // kSeedN = minima kept per (query, item): 16 or 32
+  static_assert(kSeedN == 0 || kSeedN == 16 || kSeedN == 32, "seeding keeps 16 or 32 minima");
   static_assert(kHam == 0 || (kAResident && !kDense && !kSeed), "the Hamming scan uses the resident query tile");
   constexpr int kOps = kHam != 0 ? 1 : 2;      // operand arrays in use: hi only / hi and lo
 
@@ -311,7 +314,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       int* handover = P.handover + qt * P.n_pools + slot;   // completed (warp, item) pairs of this lineage
       int cnt = 0;
       float thr = -CUDART_INF_F;
-      float top[kSeedKeep];
+      float top[kSeedN > 0 ? kSeedN : 1];
       int ham_t = -1;
       uint32_t* ham_out = nullptr;
       // kHam: this warp's epilogue group (0: warps 4..7, 1: warps 8..11) drains one of the item's two segments
@@ -327,7 +330,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         ham_out = P.ham_list + (ham_seg * P.nq + (live ? q : 0)) * P.ham_cap;
       } else if constexpr (kSeed) {
 #pragma unroll
-        for (int i = 0; i < kSeedKeep; ++i) top[i] = CUDART_INF_F;
+        for (int i = 0; i < kSeedN; ++i) top[i] = CUDART_INF_F;
       } else if (!(kDense && P.dense_only)) {
         if (gen > 0) {
           if (lane == 0) wait_counter(handover, gen * 4 * kCtaGroup);
@@ -436,7 +439,7 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           if constexpr (kSeed) {
             float x = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
 #pragma unroll
-            for (int i = 0; i < kSeedKeep; ++i) {     // sorted insertion, branch-free
+            for (int i = 0; i < kSeedN; ++i) {     // sorted insertion, branch-free
               const float lo_v = fminf(top[i], x);
               x = fmaxf(top[i], x);
               top[i] = lo_v;
@@ -521,9 +524,9 @@ flat_scan_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         if (live) P.ham_cnt[ham_seg * P.nq + q] = cnt;
       }
       if constexpr (kSeed) {
-        float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedKeep);
+        float4* out = reinterpret_cast<float4*>(P.seed_out + (q * P.n_chunks + chunk) * kSeedN);
 #pragma unroll
-        for (int i = 0; i < kSeedKeep; i += 4) out[i / 4] = make_float4(top[i], top[i + 1], top[i + 2], top[i + 3]);
+        for (int i = 0; i < kSeedN; i += 4) out[i / 4] = make_float4(top[i], top[i + 1], top[i + 2], top[i + 3]);
       } else if (kHam == 0 && !(kDense && P.dense_only)) {
         __stcg(P.pool_cnt + pool_id, cnt);
         __threadfence();                           // pool entries + count before the hand-over flag
