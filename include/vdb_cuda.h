@@ -274,6 +274,9 @@ int vdb_ivf_sq8_scan_topk(int metric, const uint8_t* list_codes, const int32_t* 
  * from the IVF k-means recipe run per sub-space by the host side.
  *   vdb_pq_encode         codes[i, s] = nearest of the 256 centroids of sub-quantiser s to x[i, s*dsub : (s+1)*dsub]
  *   vdb_pq_bias           bias[i] = |r^_i|^2 + 2 c_i . r^_i of the row's decoded residual and its list centroid (NULL = zero)
+ *   vdb_pq_decode         out[i, :] = the vector row i's code stands for (+ its list centroid; NULL = zero), fp32 [n, ld_out]:
+ *                         "PQ<m>" with many queries is searched as a flat scan over the decoded rows - the same distances
+ *                         (|q - x^|^2 / q . x^) from the tensor pipe instead of m table look-ups per (query, row)
  *   vdb_bytes_fill        scatter byte rows [n, m] - and optionally one float per row - into interleaved-32 byte lists
  *                         (layout of vdb_sq8_fill with d := m; list_values [n_blocks * 32] float)
  *   vdb_ivf_pq_scan_topk  one table per query, T[s][j] = -2 q_s . cb[s][j] (inner product: q_s . cb[s][j]), in shared memory;
@@ -283,6 +286,8 @@ int vdb_ivf_sq8_scan_topk(int metric, const uint8_t* list_codes, const int32_t* 
 int vdb_pq_encode(const float* x, int64_t n, int d, int64_t ld, const float* codebooks, int m, uint8_t* codes, void* stream);
 int vdb_pq_bias(const uint8_t* codes, int64_t n, int d, int m, const float* codebooks, const float* centroids,
                 const int32_t* assign, float* bias, void* stream);
+int vdb_pq_decode(const uint8_t* codes, int64_t n, int d, int m, const float* codebooks, const float* centroids,
+                  const int32_t* assign, float* out, int64_t ld_out, void* stream);
 int vdb_bytes_fill(const uint8_t* rows, int64_t n, int m, const int32_t* assign, const int32_t* blk_off, int nlist,
                    int32_t* cursor, uint8_t* lists, int32_t* list_ids, const float* row_values, float* list_values,
                    void* stream);

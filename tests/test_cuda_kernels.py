@@ -310,6 +310,21 @@ def test_pq_matches_oracle_given_the_same_index(eng, metric, n, d, m, nlist, k):
         ref_d, ref_i = oracle.ivf_pq_search(codes, cent, assign, books, qq, k, nprobe, mm)
         scale = float(np.linalg.norm(b, axis=1).max() * np.linalg.norm(qq, axis=1).max())
         _check((ref_d, ref_i), (D.cpu().numpy(), I.cpu().numpy()), rtol=2e-5, atol=2e-6 * scale)
+    if not nlist:
+        # "PQ<m>" with a query batch: the flat tensor-pipe scan over the DECODED rows must return what the table scan returns
+        assert shard._flat is None                       # 120 queries: the table scan ran above
+        shard.decoded_scan = "always"
+        D2, I2 = shard.search(torch.from_numpy(q.copy()).cuda(), k, 1, 0, oracle.FLT_MAX if mm == "l2" else -oracle.FLT_MAX)
+        assert shard._flat is not None and shard._flat.n == n
+        _check((ref_d, ref_i), (D2.cpu().numpy(), I2.cpu().numpy()), rtol=2e-5, atol=2e-6 * scale)
+        decoded = oracle.pq_decode(codes, books)
+        got = shard._flat.hi[:n, :d].cpu().numpy().astype(np.float64) + shard._flat.lo[:n, :d].cpu().numpy()
+        np.testing.assert_array_equal(got.astype(np.float32), decoded.astype(np.float32))       # operands = the decoded rows, exactly
+        shard.decoded_max_bytes = 1024                   # too large to keep: back to the table scan
+        shard._flat = None
+        D3, I3 = shard.search(torch.from_numpy(q.copy()).cuda(), k, 1, 0, oracle.FLT_MAX if mm == "l2" else -oracle.FLT_MAX)
+        assert shard._flat is None
+        np.testing.assert_array_equal(I3.cpu().numpy(), I.cpu().numpy())
 
 
 def test_row_utilities(eng):

@@ -75,6 +75,7 @@ SIGNATURES = {
                                      _p, _p, _i64, _p]),
     "vdb_pq_encode": (_i32, [_p, _i64, _i32, _i64, _p, _i32, _p, _p]),
     "vdb_pq_bias": (_i32, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p]),
+    "vdb_pq_decode": (_i32, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i64, _p]),
     "vdb_bytes_fill": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "vdb_ivf_pq_scan_topk": (_i32, [_i32, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f32, _i64,
                                     _p, _p, _p]),

@@ -62,6 +62,21 @@ __global__ void pq_bias_kernel(const uint8_t* __restrict__ codes, int64_t n, int
   if (lane == 0) bias[row] = static_cast<float>(acc);
 }
 
+// out[row, j] = cb[s][codes[row, s]][j - s * dsub] (+ cent[assign[row]][j]): the vector a code stands for.  thread = (row, j);
+// the codebooks (m * 256 * dsub floats: 51 KB at d = 50) stay in L1 / L2.
+__global__ void pq_decode_kernel(const uint8_t* __restrict__ codes, int64_t n, int d, int M, int dsub, const float* __restrict__ cb,
+                                 const float* __restrict__ cent, const int32_t* __restrict__ assign, float* __restrict__ out,
+                                 int64_t ld_out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t row = i / d;
+  const int j = static_cast<int>(i - row * d);
+  const int s = j / dsub;
+  float v = __ldg(cb + (static_cast<int64_t>(s) * 256 + codes[row * M + s]) * dsub + (j - s * dsub));
+  if (cent != nullptr) v += __ldg(cent + static_cast<int64_t>(assign[row]) * d + j);
+  out[row * ld_out + j] = v;
+}
+
 // scatter precomputed byte rows (and, optionally, one float per row) into the interleaved byte lists (layout of sq8.cu with
 // d := M); one warp per row
 __global__ void bytes_fill_kernel(const uint8_t* __restrict__ rows, int64_t n, int M, const int32_t* __restrict__ assign,
@@ -209,6 +224,17 @@ int vdb_pq_bias(const uint8_t* codes, int64_t n, int d, int m, const float* code
   VDB_REQUIRE(n > 0 && d > 0 && m > 0 && d % m == 0 && (centroids == nullptr || assign != nullptr), "vdb_pq_bias: bad arguments");
   pq_bias_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, n, m, d / m, codebooks,
                                                                                                         centroids, assign, bias);
+  count_launches(1);
+  VDB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vdb_pq_decode(const uint8_t* codes, int64_t n, int d, int m, const float* codebooks, const float* centroids, const int32_t* assign,
+                  float* out, int64_t ld_out, void* stream) {
+  VDB_REQUIRE(n > 0 && d > 0 && m > 0 && d % m == 0 && ld_out >= d && (centroids == nullptr || assign != nullptr),
+              "vdb_pq_decode: bad arguments");
+  pq_decode_kernel<<<static_cast<unsigned>((n * d + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      codes, n, d, m, d / m, codebooks, centroids, assign, out, ld_out);
   count_launches(1);
   VDB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -606,7 +606,18 @@ def pq_train(residuals: torch.Tensor, m: int, niter: int = 25, seed: int = 1234,
 class IVFPQShard:
     """``IVF<nlist>,PQ<m>`` (``centroids`` given) or ``PQ<m>`` (``centroids=None``: one list, zero centroid) of one GPU's
     rows: m code bytes per row - the nearest of 256 sub-centroids per sub-space of the residual x - centroid - in the
-    interleaved-32 byte lists; search builds a look-up table per (query, probed list) in shared memory."""
+    interleaved-32 byte lists; search builds a look-up table per (query, probed list) in shared memory.
+
+    ``PQ<m>`` with a batch of queries (``decoded_scan``: "auto" = 256 queries or more, "always", "never") is searched
+    as a FLAT scan over the decoded rows instead: the asymmetric distance |q - x^|^2 (q . x^) IS the flat distance to
+    the vector the code stands for, so the tensor-pipe scan + exact re-scoring returns the same neighbours without m
+    table look-ups per (query, row) - 1.2M x PQ50, 10k queries: 306 ms -> ~10 ms.  The decoded operands are built on
+    first use and kept while they fit ``decoded_max_bytes`` (they cost 8 * kpad bytes per row next to the m code
+    bytes, so a base that was quantised to FIT stays on the table scan)."""
+
+    decoded_scan = "auto"
+    decoded_min_queries = 256
+    decoded_max_bytes = 16 << 30
 
     def __init__(self, vectors, centroids, m: int, metric: str = "l2", device=None, id_offset: int = 0, codebooks=None,
                  niter: int = 25, seed: int = 1234, assign_batch: int = 1 << 18):
@@ -615,6 +626,7 @@ class IVFPQShard:
         self.metric = metric
         self.id_offset = int(id_offset)
         self.m = int(m)
+        self._flat: Optional[FlatShard] = None
         base = to_device_f32(vectors, self.dev)
         if metric == "cosine":
             base = normalized_rows(base)
@@ -700,12 +712,36 @@ class IVFPQShard:
         if (metric == "l2") != (self.list_bias is not None):
             raise RuntimeError(f"persisted PQ index was not built for metric '{metric}'")
         self.quantizer = None if self.centroids is None else FlatShard(self.centroids, "l2" if metric == "l2" else "ip", self.dev)
+        self._flat = None
         return self
+
+    def _decoded_flat(self) -> Optional[FlatShard]:
+        """Flat operands of the decoded rows (``PQ<m>`` only), or None when they would not fit ``decoded_max_bytes``."""
+        if self._flat is not None or self.quantizer is not None:
+            return self._flat
+        if self.lib.vdb_flat_npad(self.n) * self.lib.vdb_flat_kpad(self.d) * 8 > self.decoded_max_bytes:
+            return None
+        shard = self
+
+        class Decoded:                                    # rows materialised block-wise by FlatShard's upload loop
+            shape = (shard.n, shard.d)
+
+            def __getitem__(self, sl):
+                a, z = sl.start or 0, min(sl.stop, shard.n)
+                out = torch.empty((z - a, shard.d), dtype=torch.float32, device=shard.dev)
+                check(shard.lib.vdb_pq_decode(shard.codes[a:].data_ptr(), z - a, shard.d, shard.m, ptr(shard.codebooks), None, None,
+                                              ptr(out), shard.d, _stream(shard.dev)), "vdb_pq_decode")
+                return out
+
+        # the rows were normalised before they were encoded (cosine): the decoded vectors are scored as they are
+        self._flat = FlatShard(Decoded(), "l2" if self.metric == "l2" else "ip", self.dev, id_offset=self.id_offset)
+        return self._flat
 
     def memory_bytes(self) -> int:
         q = self.quantizer.memory_bytes() if self.quantizer is not None else 0
         bias = self.list_bias.numel() * 4 if self.list_bias is not None else 0
-        return self.lists.numel() + self.list_ids.numel() * 4 + bias + self.codes.numel() + self.codebooks.numel() * 4 + q
+        flat = self._flat.memory_bytes() if self._flat is not None else 0
+        return self.lists.numel() + self.list_ids.numel() * 4 + bias + self.codes.numel() + self.codebooks.numel() * 4 + q + flat
 
     def search(self, q: torch.Tensor, k: int, nprobe: int = 1, flags: int = 0, pad_value: float = FLT_MAX
                ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -715,6 +751,11 @@ class IVFPQShard:
                 q = normalized_rows(q)
             q = q.contiguous()
             probes = None
+            if (self.quantizer is None and k <= MAX_FLAT_K and self.decoded_scan != "never"
+                    and (self.decoded_scan == "always" or nq >= self.decoded_min_queries)):
+                flat = self._decoded_flat()
+                if flat is not None:
+                    return flat.search(q, k, flags, pad_value)
             if self.quantizer is None:
                 nprobe = 1                                   # IndexPQ: the single list
             else:
