@@ -111,14 +111,22 @@ def main() -> int:
         torch.cuda.synchronize()
         print(json.dumps({"algo": "pq_build", "index_key": key, "train_plus_add_s": time.time() - t0,
                           "list_bytes_per_row": int(pq._impl.m16 * 16)}), flush=True)
-        for nprobe in ((8, 32, 128) if key.startswith("IVF") else (1,)):
+        # PQ<m>: the table scan, then the flat tensor-pipe scan over the decoded rows (what a query batch gets by default)
+        for nprobe, scan in (((8, "table"), (32, "table"), (128, "table")) if key.startswith("IVF") else ((1, "table"), (1, "decoded"))):
             if hasattr(pq, "nprobe"):
                 pq.nprobe = nprobe
+            pq._impl.decoded_scan = "never" if scan == "table" else "always"
             ms_total, (D, I) = timed(lambda: pq.search_device(q_dev.clone(), k), reps=3)
             rows = (nprobe * args.n / args.nlist if key.startswith("IVF") else args.n) * args.nq
-            print(json.dumps({"algo": "pq", "index_key": key, "nprobe": nprobe, "recall@100": recall_at_k(gt, I.cpu().numpy(), 100),
-                              "ms_total": ms_total, "qps": args.nq / ms_total * 1e3, "table_lookups_per_s": rows * d / (ms_total * 1e-3)}),
-                  flush=True)
+            line = {"algo": "pq", "index_key": key, "nprobe": nprobe, "scan": scan, "recall@100": recall_at_k(gt, I.cpu().numpy(), 100),
+                    "ms_total": ms_total, "qps": args.nq / ms_total * 1e3}
+            if scan == "table":
+                line["table_lookups_per_s"] = rows * d / (ms_total * 1e-3)
+                I_table = I
+            else:
+                line["ids_equal_to_table_scan"] = float((I == I_table).float().mean().item())
+                line["decoded_operand_gb"] = pq._impl._flat.memory_bytes() / 1e9
+            print(json.dumps(line), flush=True)
         del pq
 
     lsh = indexes.GpuIndexLSH(d, 256, device=dev)
