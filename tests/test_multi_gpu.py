@@ -65,6 +65,13 @@ ivf = sharded.DistributedIVFIndex.from_global(base, 64, "l2", dev, nprobe=8)
 qd = torch.from_numpy(queries).to(dev)
 d, i = ivf.search(qd.clone(), 50)
 np.save(os.path.join({out!r}, f"d_ivf{{rank}}.npy"), d.cpu().numpy()); np.save(os.path.join({out!r}, f"i_ivf{{rank}}.npy"), i.cpu().numpy())
+# ... and with every list on every rank, the queries cut into slices (device result, then the host path)
+rep = sharded.ReplicatedIVFIndex(base, ivf.shard.centroids, "l2", dev, nprobe=8)
+d, i = rep.search(qd.clone(), 50)
+np.save(os.path.join({out!r}, f"d_ivfrep{{rank}}.npy"), d.cpu().numpy()); np.save(os.path.join({out!r}, f"i_ivfrep{{rank}}.npy"), i.cpu().numpy())
+for _ in range(2):
+    dh, ih = rep.search_host(queries, 50)
+np.save(os.path.join({out!r}, f"d_ivfrep_host{{rank}}.npy"), dh); np.save(os.path.join({out!r}, f"i_ivfrep_host{{rank}}.npy"), ih)
 if rank == 0:
     one = engine.IVFShard(base, ivf.shard.centroids, "l2", dev)
     d1, i1 = one.search(qd.clone(), 50, 8, 0, engine.FLT_MAX)
@@ -103,3 +110,6 @@ def test_distributed_flat_index_nccl(tmp_path):
     for r in range(n):        # sharded IVF == single-GPU IVF with the same centroids, on every rank
         np.testing.assert_array_equal(np.load(tmp_path / f"i_ivf{r}.npy"), np.load(tmp_path / "i_ivf_single.npy"))
         np.testing.assert_array_equal(np.load(tmp_path / f"d_ivf{r}.npy"), np.load(tmp_path / "d_ivf_single.npy"))
+        for tag in ("ivfrep", "ivfrep_host"):     # replicated lists, query slices: the same again
+            np.testing.assert_array_equal(np.load(tmp_path / f"i_{tag}{r}.npy"), np.load(tmp_path / "i_ivf_single.npy"))
+            np.testing.assert_array_equal(np.load(tmp_path / f"d_{tag}{r}.npy"), np.load(tmp_path / "d_ivf_single.npy"))

@@ -451,6 +451,54 @@ class ReplicatedFlatIndex:
         return hb.publish(ex.d_mine[:n_live], ex.i_mine[:n_live], ex.lo, nq)
 
 
+class ReplicatedIVFIndex(ReplicatedFlatIndex):
+    """IVF-Flat in the query-slice layout: every rank holds ALL the inverted lists (a C3-sized index is 0.3 GB) and
+    scans for its slice of the query batch; one allgather of the packed result blocks, or none on the host path.
+    Unlike the row layout the coarse quantiser is not repeated on every rank, so small indexes scale with the GPU
+    count.  The centroids come from rank 0 (see ``DistributedIVFIndex``); results do not depend on the order in
+    which a rank filled its lists, so they equal the one-GPU index bit for bit."""
+
+    def __init__(self, vectors, centroids, metric: str = "l2", device=None, nprobe: int = 1, group=None):
+        from . import engine
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = dist_info()
+        self.shard = engine.IVFShard(vectors, centroids, metric, device)
+        self.metric = metric
+        self.nprobe = int(nprobe)
+        self._ex = {}
+        self._host = {}
+
+    @classmethod
+    def from_global(cls, vectors, nlist: int, metric: str = "l2", device=None, nprobe: int = 1, group=None, niter: int = 10,
+                    seed: int = 1234) -> "ReplicatedIVFIndex":
+        import torch.distributed as dist
+        from . import engine
+        rank, world = dist_info()
+        dev = engine._require_cuda(device)
+        if rank == 0:
+            cent = torch.from_numpy(engine.kmeans_train(vectors, nlist, metric, dev, niter=niter, seed=seed)).to(dev)
+        else:
+            cent = torch.empty((nlist, int(vectors.shape[1])), dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(cent, src=0, group=group)
+        return cls(vectors, cent, metric, dev, nprobe=nprobe, group=group)
+
+    def _search_slice(self, q_loc: torch.Tensor, ex: TopKExchange, flags: int, pad_value: float, impl: int) -> None:
+        n_live = ex.hi - ex.lo
+        if n_live > 0:
+            d, i = self.shard.search(q_loc, ex.k, self.nprobe, flags, pad_value)
+            ex.d_mine[:n_live].copy_(d)
+            ex.i_mine[:n_live].copy_(i)
+
+    def search(self, q: torch.Tensor, k: int, flags: int = 0, pad_value: Optional[float] = None,
+               impl: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.world == 1:
+            _, pad = _conventions(self.engine, self.metric, flags, pad_value)
+            return self.shard.search(q, k, self.nprobe, flags, pad)
+        return super().search(q, k, flags, pad_value, impl)
+
+
 class DistributedIVFIndex:
     """IVF-Flat across the GPUs of one box: the centroids are replicated, rank r holds the
     inverted lists of ITS rows (every list is cut by row range), so the union of the ranks' list scans
