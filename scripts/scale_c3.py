@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE.json configs[2] (GloVe-50 shape: 1.2M x 50 fp32, cosine, 10k queries, k = 100) at 1/2/4/8 GPUs: the exact
 flat search and IVF-Flat (nlist 4096), both ROW-sharded (every rank holds the rows [lo, hi) - flat operands, or the
-inverted lists cut by row range - plus the packed top-k exchange and the merge kernel).  Strong scaling: the base is fixed.
+inverted lists cut by row range - plus the packed top-k exchange and the merge kernel); ``--layout replicated`` times
+IVF-Flat with every list on every rank and the queries cut into slices instead.  Strong scaling: the base is fixed.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/scale_c3.py
 
@@ -45,6 +46,7 @@ def main() -> int:
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--nlist", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--layout", choices=["rows", "replicated", "both"], default="rows")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -60,6 +62,26 @@ def main() -> int:
     def emit(obj):
         if rank == 0:
             print(json.dumps(dict(obj, n_gpus=world, workload=f"{args.n} x {d} fp32 cosine, {args.nq} queries, k={k}")), flush=True)
+
+    if args.layout in ("replicated", "both"):
+        # every list on every rank, the queries cut into slices: nothing is repeated per rank, one allgather of the result blocks
+        rep = sharded.ReplicatedIVFIndex.from_global(base, args.nlist, "cosine", dev)
+        whole = rep.shard                                                   # IS the one-GPU index
+        _, pad = sharded._conventions(engine, "cosine", 0, None)
+        flat1 = engine.FlatShard(base, "cosine", dev)
+        gt = flat1.search(q, k, 0, pad)[1].cpu().numpy()
+        del flat1
+        for nprobe in (8, 32, 128):
+            rep.nprobe = nprobe
+            ms, (D, I) = timed(lambda: rep.search(q, k), dev, world, args.steps)
+            D1, I1 = whole.search(q, k, nprobe, 0, pad)
+            emit({"algo": "ivf_flat_replicated", "nlist": args.nlist, "nprobe": nprobe, "ms_per_step": ms, "qps": args.nq / ms * 1e3,
+                  "recall@100": recall_at_k(gt, I.cpu().numpy(), 100), "equals_one_gpu_index": bool(torch.equal(I1, I) and torch.equal(D1, D))})
+        del rep, whole
+        if args.layout == "replicated":
+            if world > 1:
+                dist.destroy_process_group()
+            return 0
 
     flat = sharded.DistributedFlatIndex.from_global(base, "cosine", dev)
     ms, (D, I) = timed(lambda: flat.search(q, k), dev, world, args.steps)
