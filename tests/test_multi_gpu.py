@@ -72,6 +72,16 @@ np.save(os.path.join({out!r}, f"d_ivfrep{{rank}}.npy"), d.cpu().numpy()); np.sav
 for _ in range(2):
     dh, ih = rep.search_host(queries, 50)
 np.save(os.path.join({out!r}, f"d_ivfrep_host{{rank}}.npy"), dh); np.save(os.path.join({out!r}, f"i_ivfrep_host{{rank}}.npy"), ih)
+# the same two layouts behind the plugin API (ApproximateSearch under torchrun), with the centroids of rank 0
+for mode in ("queries", "rows"):
+    algo = A.get_algorithm_instance("ApproximateSearch", 48, name="ivf", index_type="IVF64,Flat", metric="l2", nprobe=8, device=dev, shard=mode)
+    algo.build_index(base)
+    da, ia = algo.batch_search(queries, 50)
+    one = engine.IVFShard(base, algo.index.centroids, "l2", dev)
+    d1, i1 = one.search(qd.clone(), 50, 8, 0, engine.FLT_MAX)
+    assert np.array_equal(ia, i1.cpu().numpy()) and np.array_equal(da, d1.cpu().numpy()), mode
+    assert type(algo.index._dist).__name__ == ("ReplicatedIVFIndex" if mode == "queries" else "DistributedIVFIndex")
+    del algo, one
 if rank == 0:
     one = engine.IVFShard(base, ivf.shard.centroids, "l2", dev)
     d1, i1 = one.search(qd.clone(), 50, 8, 0, engine.FLT_MAX)

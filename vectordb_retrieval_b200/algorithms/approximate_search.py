@@ -32,7 +32,10 @@ class ApproximateSearch(BaseAlgorithm):
         if vectors.ndim != 2 or vectors.shape[1] != self.dimension:
             raise RuntimeError(f"expected vectors of shape [n, {self.dimension}], got {vectors.shape}")
         self.vectors = vectors
-        self.index = index_factory(self.dimension, self.index_type, self.metric, device=self.config.get("device"))
+        extra = {"shard": self.config["shard"]} if "shard" in self.config else {}     # torchrun: 'rows' / 'queries' / 'auto'
+        self.index = index_factory(self.dimension, self.index_type, self.metric, device=self.config.get("device"), **extra)
+        if "nprobe" in self.config:
+            self.index.nprobe = int(self.config["nprobe"])
         if not self.index.is_trained:
             self.index.train(vectors)
         self.index.add(vectors)

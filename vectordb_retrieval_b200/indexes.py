@@ -121,9 +121,14 @@ class GpuIndexIVFFlat:
     search top-``nprobe`` centroids per query, scan of those lists with exact scoring."""
 
     def __init__(self, d: int, nlist: int, metric="l2", device=None, niter: int = 10, seed: int = 1234,
-                 max_points_per_centroid: int = 256, centroids: Optional[np.ndarray] = None, normalize: bool = False):
+                 max_points_per_centroid: int = 256, centroids: Optional[np.ndarray] = None, normalize: bool = False,
+                 shard: str = "auto"):
         if nlist <= 0:
             raise ValueError("nlist must be positive")
+        if shard not in ("auto", "rows", "queries"):
+            raise ValueError(f"shard must be 'auto', 'rows' or 'queries', got '{shard}'")
+        self.shard = shard                    # under torchrun (IVF-Flat): lists cut by row range, or every list on every rank
+        self._dist = None
         self.d, self.nlist = int(d), int(nlist)
         self.metric = _metric_name(metric)
         self.normalize = bool(normalize)
@@ -138,8 +143,23 @@ class GpuIndexIVFFlat:
     def train(self, x) -> None:
         if self.is_trained:
             return
-        self.centroids = engine.kmeans_train(x, self.nlist, self._engine_metric(), self.device, niter=self.niter, seed=self.seed,
-                                             max_points_per_centroid=self.max_points_per_centroid)
+        from . import sharded
+        rank, world = sharded.dist_info()
+        if world > 1:
+            # one process per GPU: rank 0 trains, everyone gets ITS centroids (k-means accumulates with float atomics,
+            # so two ranks training on the same sample would not agree bit for bit)
+            import torch.distributed as dist
+            dev = engine._require_cuda(self.device)
+            if rank == 0:
+                cent = torch.from_numpy(engine.kmeans_train(x, self.nlist, self._engine_metric(), dev, niter=self.niter, seed=self.seed,
+                                                            max_points_per_centroid=self.max_points_per_centroid)).to(dev)
+            else:
+                cent = torch.empty((self.nlist, self.d), dtype=torch.float32, device=dev)
+            dist.broadcast(cent, src=0)
+            self.centroids = cent.cpu().numpy()
+        else:
+            self.centroids = engine.kmeans_train(x, self.nlist, self._engine_metric(), self.device, niter=self.niter, seed=self.seed,
+                                                 max_points_per_centroid=self.max_points_per_centroid)
         self.is_trained = True
 
     def _engine_metric(self) -> str:
@@ -150,8 +170,25 @@ class GpuIndexIVFFlat:
             raise RuntimeError("GpuIndexIVFFlat.add before train")
         if self._impl is not None:
             raise RuntimeError("GpuIndexIVFFlat.add may be called once")
-        self._impl = engine.IVFShard(x, self.centroids, self._engine_metric(), self.device)
+        from . import sharded
+        rank, world = sharded.dist_info()
         self.ntotal = int(x.shape[0])
+        if world > 1:
+            # 'queries' (auto while the lists stay under 8 GB): every list on every rank, each rank scans for its slice of
+            # the batch; 'rows': the lists cut by row range + the packed top-k exchange + merge kernel
+            layout = self.shard if self.shard != "auto" else ("queries" if 4.0 * self.ntotal * self.d <= 8e9 else "rows")
+            if layout == "queries":
+                self._dist = sharded.ReplicatedIVFIndex(x, self.centroids, self._engine_metric(), self.device, nprobe=self.nprobe)
+            else:
+                plan = sharded.ShardPlan(self.ntotal, world)
+                lo, hi = plan.start(rank), plan.stop(rank)
+                if hi <= lo:
+                    raise RuntimeError(f"rank {rank} of {world} owns no rows of a {self.ntotal}-row base")
+                self._dist = sharded.DistributedIVFIndex(x[lo:hi], self.centroids, self._engine_metric(), self.device, id_offset=lo,
+                                                         nprobe=self.nprobe)
+            self._impl = self._dist.shard
+            return
+        self._impl = engine.IVFShard(x, self.centroids, self._engine_metric(), self.device)
 
     @property
     def home(self) -> torch.device:
@@ -164,6 +201,8 @@ class GpuIndexIVFFlat:
         from . import persist
         if self._impl is None:
             raise RuntimeError("index is empty")
+        if self._dist is not None:
+            raise RuntimeError("a sharded IVF index is not persisted: save from a single-process index")
         meta = {"d": self.d, "nlist": self.nlist, "metric": self.metric, "normalize": self.normalize,
                 "nprobe": int(self.nprobe), "ntotal": self.ntotal}
         return persist.write_artifact(artifact_dir, "ivf_flat", self._impl.state(), meta, context)
@@ -183,12 +222,19 @@ class GpuIndexIVFFlat:
         if self._impl is None:
             raise RuntimeError("index is empty")
         pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+        if self._dist is not None:
+            self._dist.nprobe = int(self.nprobe)
+            return self._dist.search(q, k, 0, pad)
         return self._impl.search(q, k, int(self.nprobe), 0, pad)
 
     def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
         if self._impl is None:
             raise RuntimeError("index is empty")
         with torch.cuda.device(self.home):
+            if self._dist is not None and hasattr(self._dist, "search_host"):     # query slices: only this rank's slice moves
+                self._dist.nprobe = int(self.nprobe)
+                pad = engine.FLT_MAX if self.metric == "l2" else -engine.FLT_MAX
+                return self._dist.search_host(queries, int(k), 0, pad)
             q = engine.queries_to_device(queries, self.home, self.d)
             return engine.results_to_host(*self.search_device(q, int(k)))
 
