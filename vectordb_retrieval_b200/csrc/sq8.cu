@@ -80,6 +80,14 @@ __global__ void sq8_fill_kernel(const float* __restrict__ x, int64_t n, int d, i
   if (lane == 0) ids[b * 32 + v] = static_cast<int32_t>(row);
 }
 
+// Byte B of w as a float, exactly, without the conversion unit: PRMT drops the byte into the mantissa of 2^23 (ALU pipe), one
+// FADD removes the 2^23.  I2F runs on the quarter-rate XU pipe, which the first version of the scan kept 69 % busy
+// (profiles/r2/sq8_scan_np32_r3p.md) - its top pipe, ahead of FMA and LSU.
+template <int B>
+__device__ __forceinline__ float byte_as_float(uint32_t w) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | B)) - 8388608.f;
+}
+
 // W warps per query, TW / W queries per CTA (see ivf.cu).  Per probed list the group stages, in shared memory,
 //   L2: t_j = (q_j - c_j) - (vmin_j + 0.5 vdiff_j / 255)  so that  dist = sum_j (t_j - s_j code_j)^2,  s_j = vdiff_j / 255
 //   IP: w_j = q_j s_j (once per query) and the scalar  q.c + sum_j q_j (vmin_j + 0.5 s_j)  so that  score = scalar + sum_j w_j code_j
@@ -156,8 +164,8 @@ ivf_sq8_scan_kernel(int metric, const uint4* __restrict__ codes, const int32_t* 
           for (int h = 0; h < 4; ++h) {
             const int j = (c0 + i) * 16 + h * 4;
             const float4 s4 = *reinterpret_cast<const float4*>(sv + j);
-            const float c0f = static_cast<float>(wds[h] & 0xffu), c1f = static_cast<float>((wds[h] >> 8) & 0xffu);
-            const float c2f = static_cast<float>((wds[h] >> 16) & 0xffu), c3f = static_cast<float>(wds[h] >> 24);
+            const float c0f = byte_as_float<0>(wds[h]), c1f = byte_as_float<1>(wds[h]);
+            const float c2f = byte_as_float<2>(wds[h]), c3f = byte_as_float<3>(wds[h]);
             if (l2) {
               const float4 t4 = *reinterpret_cast<const float4*>(tv + j);
               const float e0 = fmaf(-s4.x, c0f, t4.x), e1 = fmaf(-s4.y, c1f, t4.y), e2 = fmaf(-s4.z, c2f, t4.z), e3 = fmaf(-s4.w, c3f, t4.w);
